@@ -1,0 +1,342 @@
+// extern "C" entry points of libegnn_b200.so (see include/egnn_b200.h) and the per-layer
+// orchestration: [neighbour select] -> per-node tables -> fused edge kernel -> node update.
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "fast_path.h"
+#include "profile.h"
+
+namespace egnn {
+
+int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
+                        const uint8_t* adj, int adj_batched, float valid_radius, int32_t* out_idx,
+                        uint8_t* out_ok, cudaStream_t st);
+
+// ------------------------------------------------------------------ validation
+static int validate_desc(const EgnnLayerDesc* d) {
+  if (!d) return EGNN_ERR_NULL;
+  if (d->abi_version != EGNN_ABI_VERSION) return EGNN_ERR_ABI;
+  if (d->dtype != EGNN_DTYPE_F32 && d->dtype != EGNN_DTYPE_F64 && d->dtype != EGNN_DTYPE_BF16)
+    return EGNN_ERR_UNSUPPORTED;
+  if (d->B <= 0 || d->N <= 0 || d->dim <= 0 || d->C <= 0 || d->edge_dim < 0 || d->label_dim < 0 ||
+      d->fourier < 0 || d->m_dim <= 0 || d->k < 0)
+    return EGNN_ERR_SHAPE;
+  if (d->B > 65535) return EGNN_ERR_SHAPE;
+  if (d->C > PAIR_CMAX) return EGNN_ERR_UNSUPPORTED;
+  if (d->m_dim > 32) return EGNN_ERR_UNSUPPORTED;
+  if (d->fourier > 30) return EGNN_ERR_UNSUPPORTED;
+  if (d->k > d->N) return EGNN_ERR_SHAPE;                 // torch.topk raises too (:258)
+  if (d->label_dim > 0 && (d->num_labels <= 0 || d->num_labels > 255)) return EGNN_ERR_SHAPE;
+  if (!(d->flags & (EGNN_FLAG_UPDATE_FEATS | EGNN_FLAG_UPDATE_COORS))) return EGNN_ERR_SHAPE;   // :171
+  if (d->row_begin < 0 || d->row_end < 0 || d->row_end > d->N || d->row_begin > d->row_end) return EGNN_ERR_SHAPE;
+  return EGNN_OK;
+}
+
+static inline size_t elem_size(int dtype) { return dtype == EGNN_DTYPE_F64 ? 8 : (dtype == EGNN_DTYPE_F32 ? 4 : 2); }
+
+// ------------------------------------------------------------------ SIMT workspace
+struct SimtWs {
+  size_t P, node_in, h1, nbr_idx, nbr_ok, total;
+};
+static SimtWs simt_ws_layout(const Dims& s, size_t es, uint32_t flags) {
+  SimtWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += round_up(bytes, 256); return r; };
+  w.P = take((size_t)s.M * 2 * s.Hp * es);
+  const bool uf = flags & EGNN_FLAG_UPDATE_FEATS;
+  w.node_in = take(uf ? (size_t)s.M * (s.dim + s.m) * es : 0);
+  w.h1 = take(uf ? (size_t)s.M * 2 * s.dim * es : 0);
+  w.nbr_idx = take((size_t)s.M * s.k * sizeof(int32_t));
+  w.nbr_ok = take((size_t)s.M * s.k);
+  w.total = o;
+  return w;
+}
+
+template <typename T, int ACT, bool RES>
+static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, const T* R, int ldr, T* C,
+                       int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st) {
+  dim3 grid(ceil_div(Nout, 64), ceil_div(Mr, 64));
+  gemm_nt_kernel<T, ACT, RES><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+  EGNN_LAUNCH_CHECK();
+  count_launch();
+  return EGNN_OK;
+}
+
+template <typename T, int MP, bool KNN>
+static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
+  const size_t smem = pair_smem_bytes<T>(a.s, a.L, KNN);
+  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
+  EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_kernel<T, MP, KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int TI = PAIR_THREADS / a.TS;
+  dim3 grid(ceil_div(a.s.row1 - a.s.row0, TI), a.s.B);
+  pair_kernel<T, MP, KNN><<<grid, PAIR_THREADS, smem, st>>>(a);
+  EGNN_LAUNCH_CHECK();
+  count_launch();
+  return EGNN_OK;
+}
+
+template <typename T>
+static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* packed,
+                        const EgnnLayerIO& io, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const Dims s = make_dims(d);
+  const SimtPackLayout L = simt_pack_layout(s);
+  const SimtWs wl = simt_ws_layout(s, sizeof(T), d.flags);
+  if (ws_bytes < wl.total) return EGNN_ERR_WORKSPACE;
+  if (s.row1 <= s.row0) return EGNN_OK;
+  char* base = static_cast<char*>(ws);
+  T* P = reinterpret_cast<T*>(base + wl.P);
+  T* node_in = reinterpret_cast<T*>(base + wl.node_in);
+  T* h1 = reinterpret_cast<T*>(base + wl.h1);
+  int32_t* nbr_idx = reinterpret_cast<int32_t*>(base + wl.nbr_idx);
+  uint8_t* nbr_ok = reinterpret_cast<uint8_t*>(base + wl.nbr_ok);
+  const T* feats = static_cast<const T*>(io.feats);
+  const T* W1 = static_cast<const T*>(w.edge_w1);
+  const bool uf = d.flags & EGNN_FLAG_UPDATE_FEATS, uc = d.flags & EGNN_FLAG_UPDATE_COORS;
+  const RowMap ident{s.N, s.N, 0};
+
+  // 1. neighbour lists (egnn_pytorch.py:237-260)
+  if (s.k > 0) {
+    StageTimer tm(st, STAGE_SELECT);
+    count_launch();
+    const float vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0f : d.valid_radius;     // :250
+    EGNN_TRY(knn_select_dispatch(d.dtype, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
+                                 (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
+  }
+  // 2. per-node tables  A = h W1[:, :dim]^T + b1,  B = h W1[:, dim:2dim]^T   (split of :287's Linear-1)
+  {
+    StageTimer tm(st, STAGE_NODE_PRE);
+    EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1, s.E, static_cast<const T*>(w.edge_b1), nullptr, 0, P,
+                                        2 * s.Hp, s.M, s.H, s.Hp, s.dim, ident, st)));
+    EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1 + s.dim, s.E, nullptr, nullptr, 0, P + s.Hp, 2 * s.Hp,
+                                        s.M, s.H, s.Hp, s.dim, ident, st)));
+  }
+  // 3. fused edge step
+  PairArgs<T> a;
+  a.s = s; a.L = L; a.flags = d.flags; a.has_mask = io.mask != nullptr;
+  a.clamp = (T)d.clamp;
+  a.P = P; a.ldP = 2 * s.Hp;
+  a.coors = static_cast<const T*>(io.coors);
+  a.edges = static_cast<const T*>(io.edges);
+  a.labels = s.label_dim > 0 ? io.edge_labels : nullptr;
+  a.mask = io.mask;
+  a.nbr_idx = nbr_idx; a.nbr_ok = nbr_ok;
+  a.packed = static_cast<const T*>(packed);
+  a.m_out = uf ? node_in + s.dim : nullptr;
+  a.ld_m = s.dim + s.m;
+  a.coors_out = uc ? static_cast<T*>(io.coors_out) : nullptr;
+  {
+    StageTimer tm(st, STAGE_PAIR);
+    if (s.k > 0) {
+      int TS = 1;
+      while (TS < s.k && TS < 32) TS <<= 1;
+      a.TS = TS;
+      if (L.MP == 16) EGNN_TRY((launch_pair<T, 16, true>(a, st)));
+      else EGNN_TRY((launch_pair<T, 32, true>(a, st)));
+    } else {
+      a.TS = 32;
+      if (L.MP == 16) EGNN_TRY((launch_pair<T, 16, false>(a, st)));
+      else EGNN_TRY((launch_pair<T, 32, false>(a, st)));
+    }
+  }
+  // 4. node update  h' = node_mlp([LN(h) | m_i]) + h   (egnn_pytorch.py:335-337)
+  StageTimer post_tm(st, STAGE_NODE_POST);
+  const int Rr = s.row1 - s.row0, Mr = s.B * Rr;
+  const RowMap map{Rr, s.N, s.row0};
+  if (uf) {
+    ln_concat_kernel<T><<<ceil_div(Mr * 32, 256), 256, 0, st>>>(
+        feats, static_cast<const T*>(w.norm_g), static_cast<const T*>(w.norm_b), node_in, s.dim + s.m, s.dim, Mr,
+        map, (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0);
+    EGNN_LAUNCH_CHECK();
+    count_launch();
+    EGNN_TRY((launch_gemm<T, 1, false>(node_in, s.dim + s.m, static_cast<const T*>(w.node_w1), s.dim + s.m,
+                                       static_cast<const T*>(w.node_b1), nullptr, 0, h1, 2 * s.dim, Mr, 2 * s.dim,
+                                       2 * s.dim, s.dim + s.m, map, st)));
+    EGNN_TRY((launch_gemm<T, 0, true>(h1, 2 * s.dim, static_cast<const T*>(w.node_w2), 2 * s.dim,
+                                      static_cast<const T*>(w.node_b2), feats, s.dim, static_cast<T*>(io.feats_out),
+                                      s.dim, Mr, s.dim, s.dim, 2 * s.dim, map, st)));
+  } else if (io.feats_out != io.feats) {
+    EGNN_CUDA_TRY(cudaMemcpyAsync(io.feats_out, io.feats, (size_t)s.M * s.dim * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  }
+  if (!uc && io.coors_out != io.coors)
+    EGNN_CUDA_TRY(cudaMemcpyAsync(io.coors_out, io.coors, (size_t)s.M * s.C * sizeof(T), cudaMemcpyDeviceToDevice, st));
+  return EGNN_OK;
+}
+
+static int check_ptrs(const EgnnLayerDesc& d, const EgnnLayerWeights* w, const EgnnLayerIO* io) {
+  if (!w || !w->edge_w1 || !w->edge_b1 || !w->edge_w2 || !w->edge_b2) return EGNN_ERR_NULL;
+  if ((d.flags & EGNN_FLAG_SOFT_EDGES) && (!w->gate_w || !w->gate_b)) return EGNN_ERR_NULL;
+  if ((d.flags & EGNN_FLAG_NORM_FEATS) && (d.flags & EGNN_FLAG_UPDATE_FEATS) && (!w->norm_g || !w->norm_b)) return EGNN_ERR_NULL;
+  if ((d.flags & EGNN_FLAG_NORM_COORS) && !w->coors_scale) return EGNN_ERR_NULL;
+  if ((d.flags & EGNN_FLAG_UPDATE_FEATS) && (!w->node_w1 || !w->node_b1 || !w->node_w2 || !w->node_b2)) return EGNN_ERR_NULL;
+  if ((d.flags & EGNN_FLAG_UPDATE_COORS) && (!w->coors_w1 || !w->coors_b1 || !w->coors_w2 || !w->coors_b2)) return EGNN_ERR_NULL;
+  if (d.label_dim > 0 && !w->label_emb) return EGNN_ERR_NULL;
+  if (io) {
+    if (!io->feats || !io->coors || !io->feats_out || !io->coors_out) return EGNN_ERR_NULL;
+    if (d.edge_dim > 0 && !io->edges) return EGNN_ERR_NULL;
+    if (d.label_dim > 0 && !io->edge_labels) return EGNN_ERR_NULL;
+    const uintptr_t all = (uintptr_t)io->feats | (uintptr_t)io->feats_out | (uintptr_t)io->edges;
+    if (all & 0xF) return EGNN_ERR_ALIGN;
+  }
+  return EGNN_OK;
+}
+
+}  // namespace egnn
+
+using namespace egnn;
+
+extern "C" int egnn_abi_version(void) { return EGNN_ABI_VERSION; }
+
+extern "C" const char* egnn_strerror(int code) {
+  switch (code) {
+    case EGNN_OK: return "ok";
+    case EGNN_ERR_NULL: return "required pointer is NULL";
+    case EGNN_ERR_SHAPE: return "inconsistent or out-of-range sizes";
+    case EGNN_ERR_UNSUPPORTED: return "option combination not supported by this build";
+    case EGNN_ERR_ALIGN: return "pointer not 16-byte aligned";
+    case EGNN_ERR_WORKSPACE: return "workspace or packed-parameter buffer too small";
+    case EGNN_ERR_ABI: return "ABI version mismatch";
+    default: break;
+  }
+  if (code <= EGNN_ERR_CUDA) return cudaGetErrorString((cudaError_t)(EGNN_ERR_CUDA - code));
+  return "unknown error";
+}
+
+extern "C" int egnn_layer_packed_bytes(const EgnnLayerDesc* desc, size_t* out_bytes) {
+  if (!out_bytes) return EGNN_ERR_NULL;
+  EGNN_TRY(validate_desc(desc));
+  const Dims s = make_dims(*desc);
+  if (desc->dtype == EGNN_DTYPE_BF16) return fast_packed_bytes(*desc, out_bytes);
+  *out_bytes = round_up(simt_pack_layout(s).total * elem_size(desc->dtype), 256);
+  return EGNN_OK;
+}
+
+extern "C" int egnn_layer_pack_weights(const EgnnLayerDesc* desc, const EgnnLayerWeights* w, void* packed,
+                                       size_t packed_bytes, void* stream) {
+  EGNN_TRY(validate_desc(desc));
+  if (!packed) return EGNN_ERR_NULL;
+  EGNN_TRY(check_ptrs(*desc, w, nullptr));
+  size_t need = 0;
+  EGNN_TRY(egnn_layer_packed_bytes(desc, &need));
+  if (packed_bytes < need) return EGNN_ERR_WORKSPACE;
+  if ((uintptr_t)packed & 0xF) return EGNN_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dims s = make_dims(*desc);
+  if (desc->dtype == EGNN_DTYPE_BF16) return fast_pack_weights(*desc, *w, packed, packed_bytes, st);
+  const SimtPackLayout L = simt_pack_layout(s);
+  if (desc->dtype == EGNN_DTYPE_F64)
+    simt_pack_kernel<double><<<148, 256, 0, st>>>(s, L, *w, desc->flags, static_cast<double*>(packed));
+  else
+    simt_pack_kernel<float><<<148, 256, 0, st>>>(s, L, *w, desc->flags, static_cast<float*>(packed));
+  EGNN_LAUNCH_CHECK();
+  return EGNN_OK;
+}
+
+extern "C" int egnn_layer_workspace_bytes(const EgnnLayerDesc* desc, size_t* out_bytes) {
+  if (!out_bytes) return EGNN_ERR_NULL;
+  EGNN_TRY(validate_desc(desc));
+  const Dims s = make_dims(*desc);
+  if (desc->dtype == EGNN_DTYPE_BF16) return fast_workspace_bytes(*desc, out_bytes);
+  *out_bytes = simt_ws_layout(s, elem_size(desc->dtype), desc->flags).total + 256;
+  return EGNN_OK;
+}
+
+extern "C" int egnn_layer_forward(const EgnnLayerDesc* desc, const EgnnLayerWeights* w, const void* packed,
+                                  const EgnnLayerIO* io, void* workspace, size_t workspace_bytes, void* stream) {
+  EGNN_TRY(validate_desc(desc));
+  if (!io || !packed || !workspace) return EGNN_ERR_NULL;
+  EGNN_TRY(check_ptrs(*desc, w, io));
+  if ((uintptr_t)workspace & 0xFF) return EGNN_ERR_ALIGN;
+  if ((uintptr_t)packed & 0xF) return EGNN_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (desc->dtype) {
+    case EGNN_DTYPE_F64: return simt_forward<double>(*desc, *w, packed, *io, workspace, workspace_bytes, st);
+    case EGNN_DTYPE_F32: return simt_forward<float>(*desc, *w, packed, *io, workspace, workspace_bytes, st);
+    case EGNN_DTYPE_BF16: return fast_forward(*desc, *w, packed, *io, workspace, workspace_bytes, st);
+    default: return EGNN_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLayerWeights* w, const void* packed,
+                                       const EgnnLayerIO* hio, void* stream) {
+  EGNN_TRY(validate_desc(desc));
+  if (!hio || !packed) return EGNN_ERR_NULL;
+  if (!hio->feats || !hio->coors || !hio->feats_out || !hio->coors_out) return EGNN_ERR_NULL;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const Dims s = make_dims(*desc);
+  const size_t es = elem_size(desc->dtype);
+  const size_t cs = desc->dtype == EGNN_DTYPE_F64 ? 8 : 4;
+  const size_t nf = (size_t)s.M * s.dim * es, nc = (size_t)s.M * s.C * cs;
+  const size_t ne = hio->edges ? (size_t)s.M * s.N * s.edge_dim * es : 0;
+  const size_t nl = hio->edge_labels ? (size_t)s.M * s.N : 0;
+  const size_t nm = hio->mask ? (size_t)s.M : 0;
+  const size_t na = hio->adj ? (size_t)((desc->flags & EGNN_FLAG_ADJ_BATCHED) ? s.B : 1) * s.N * s.N : 0;
+  size_t wsb = 0;
+  EGNN_TRY(egnn_layer_workspace_bytes(desc, &wsb));
+  // one device arena: [feats | feats_out | coors | coors_out | edges | labels | mask | adj | workspace]
+  size_t off[10];
+  size_t o = 0;
+  const size_t sizes[9] = {nf, nf, nc, nc, ne, nl, nm, na, wsb};
+  for (int i = 0; i < 9; ++i) { off[i] = o; o += round_up(sizes[i], 256); }
+  char* arena = nullptr;
+  EGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&arena), o + 256, st));
+  int rc = EGNN_OK;
+  auto h2d = [&](int slot, const void* src, size_t n) {
+    if (n && rc == EGNN_OK) {
+      cudaError_t e = cudaMemcpyAsync(arena + off[slot], src, n, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) rc = EGNN_ERR_CUDA - (int)e;
+    }
+  };
+  h2d(0, hio->feats, nf); h2d(2, hio->coors, nc); h2d(4, hio->edges, ne); h2d(5, hio->edge_labels, nl);
+  h2d(6, hio->mask, nm); h2d(7, hio->adj, na);
+  if (rc == EGNN_OK) {
+    EgnnLayerIO dio;
+    dio.feats = arena + off[0]; dio.feats_out = arena + off[1];
+    dio.coors = arena + off[2]; dio.coors_out = arena + off[3];
+    dio.edges = ne ? arena + off[4] : nullptr;
+    dio.edge_labels = nl ? reinterpret_cast<uint8_t*>(arena + off[5]) : nullptr;
+    dio.mask = nm ? reinterpret_cast<uint8_t*>(arena + off[6]) : nullptr;
+    dio.adj = na ? reinterpret_cast<uint8_t*>(arena + off[7]) : nullptr;
+    rc = egnn_layer_forward(desc, w, packed, &dio, arena + off[8], wsb, stream);
+  }
+  if (rc == EGNN_OK) {
+    cudaError_t e = cudaMemcpyAsync(hio->feats_out, arena + off[1], nf, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hio->coors_out, arena + off[3], nc, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = EGNN_ERR_CUDA - (int)e;
+  }
+  cudaFreeAsync(arena, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == EGNN_OK && e != cudaSuccess) rc = EGNN_ERR_CUDA - (int)e;
+  return rc;
+}
+
+// ---- diagnostics (see profile.h): per-stage CUDA-event timing on the launch stream ----------
+extern "C" int egnn_profile_enable(int on) {
+  Profiler& p = Profiler::get();
+  std::lock_guard<std::mutex> g(p.mu);
+  p.on = on != 0;
+  return EGNN_OK;
+}
+
+extern "C" int egnn_profile_read(float* ms_out, int32_t* spans_out, int64_t* launches_out, int reset) {
+  Profiler& p = Profiler::get();
+  std::lock_guard<std::mutex> g(p.mu);
+  float ms[STAGE_COUNT] = {0, 0, 0, 0};
+  int32_t n[STAGE_COUNT] = {0, 0, 0, 0};
+  for (auto& sp : p.spans) {
+    EGNN_CUDA_TRY(cudaEventSynchronize(sp.b));
+    float t = 0.f;
+    EGNN_CUDA_TRY(cudaEventElapsedTime(&t, sp.a, sp.b));
+    ms[sp.stage] += t;
+    n[sp.stage] += 1;
+  }
+  for (int i = 0; i < STAGE_COUNT; ++i) {
+    if (ms_out) ms_out[i] = ms[i];
+    if (spans_out) spans_out[i] = n[i];
+  }
+  if (launches_out) *launches_out = p.launches;
+  if (reset) {
+    for (auto& sp : p.spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    p.spans.clear();
+    p.launches = 0;
+  }
+  return EGNN_OK;
+}

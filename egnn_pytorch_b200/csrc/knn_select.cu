@@ -1,0 +1,225 @@
+// Neighbour ranking + top-k select fused into the distance pass
+// (reference egnn_pytorch.py:232-233 all-pairs distance, :237-260 ranking and topk).
+//
+//   rank(i,j) = ||x_i - x_j||^2
+//             = 1e5   if a mask is given and either end is padded            (:240-242)
+//             = -1    if an adjacency is given and i == j                      (:255)
+//             = 0     if an adjacency is given and adj[i,j], i != j            (:256)
+//   keep the k smallest (rank, j) pairs in ascending lexicographic order -> deterministic
+//   "lowest index wins" tie rule (torch.topk leaves ties unspecified).
+//
+// k <= 32: one warp per row keeps the running top-32 sorted across its lanes; candidates that
+// beat the current k-th entry are queued in shared memory and merged 32 at a time with a
+// warp-bitonic sort + merge, so the O(N^2) ranking matrix is never written.
+// k  > 32: one block per row sorts all N (rank, j) pairs in shared memory (bitonic).
+#include "common.cuh"
+
+namespace egnn {
+
+template <typename T>
+struct SelArgs {
+  int B, N, C, k;
+  const T* coors;
+  const uint8_t* mask;
+  const uint8_t* adj;
+  int adj_batched;
+  T valid_radius;
+  int32_t* out_idx;
+  uint8_t* out_ok;
+};
+
+template <typename T>
+__device__ __forceinline__ T rank_of(const SelArgs<T>& a, int b, int i, int j, const T* xi, bool mask_i) {
+  const T* xj = a.coors + ((size_t)b * a.N + j) * a.C;
+  T d = T(0);
+  for (int c = 0; c < a.C; ++c) { T r = xi[c] - xj[c]; d += r * r; }
+  if (a.mask && !(mask_i && a.mask[(size_t)b * a.N + j])) d = T(1e5);
+  if (a.adj) {
+    if (i == j) d = T(-1);
+    else if (a.adj[((size_t)(a.adj_batched ? b : 0) * a.N + i) * a.N + j]) d = T(0);
+  }
+  return d;
+}
+
+template <typename T>
+__device__ __forceinline__ bool lex_less(T ka, int ia, T kb, int ib) {
+  return ka < kb || (ka == kb && ia < ib);
+}
+
+// One compare-exchange step of a warp bitonic network on (key, idx) pairs.
+template <typename T>
+__device__ __forceinline__ void cmpex(T& key, int& idx, int lane, int partner_xor, bool ascending_block) {
+  T ok = shfl_xor_t<T>(key, partner_xor);
+  int oi = __shfl_xor_sync(0xffffffffu, idx, partner_xor);
+  const bool lower = (lane & partner_xor) == 0;
+  const bool other_less = lex_less<T>(ok, oi, key, idx);
+  // in an ascending block the lower lane keeps the min
+  const bool take_other = (lower == ascending_block) ? other_less : !other_less && !(ok == key && oi == idx);
+  if (take_other) { key = ok; idx = oi; }
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_sort_asc(T& key, int& idx, int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+    const bool asc = (lane & size) == 0 || size == 32;
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) cmpex<T>(key, idx, lane, stride, asc);
+  }
+}
+
+// best (sorted ascending across lanes) <- the 32 smallest of best U cand.
+template <typename T>
+__device__ __forceinline__ void warp_merge(T& bkey, int& bidx, T ckey, int cidx, int lane) {
+  warp_sort_asc<T>(ckey, cidx, lane);
+  // reverse the candidates so that best ++ reversed(cand) is bitonic; lane l meets cand[31-l]
+  T rk = shfl_idx_t<T>(ckey, 31 - lane);
+  int ri = __shfl_sync(0xffffffffu, cidx, 31 - lane);
+  if (lex_less<T>(rk, ri, bkey, bidx)) { bkey = rk; bidx = ri; }
+  // the kept 32 form a bitonic sequence: finish with the 5 merge steps
+#pragma unroll
+  for (int stride = 16; stride > 0; stride >>= 1) cmpex<T>(bkey, bidx, lane, stride, true);
+}
+
+constexpr int SEL_WARPS = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+knn_warp_select_kernel(const SelArgs<T> a) {
+  __shared__ T qkey[SEL_WARPS][64];
+  __shared__ int qidx[SEL_WARPS][64];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * SEL_WARPS + warp;     // b*N + i
+  if (row >= a.B * a.N) return;
+  const int b = row / a.N, i = row % a.N;
+  const T* xi = a.coors + (size_t)row * a.C;
+  const bool mask_i = a.mask ? a.mask[row] != 0 : true;
+  const T INF = T(INFINITY);
+  const int IMAX = 0x7fffffff;
+
+  T bkey = INF; int bidx = IMAX;       // lane l: l-th smallest so far
+  T thr_key = INF; int thr_idx = IMAX; // the k-th smallest so far
+  int count = 0;                       // queued candidates (warp-uniform)
+
+  for (int j0 = 0; j0 < a.N; j0 += 32) {
+    const int j = j0 + lane;
+    T key = INF;
+    if (j < a.N) key = rank_of<T>(a, b, i, j, xi, mask_i);
+    const bool pass = j < a.N && lex_less<T>(key, j, thr_key, thr_idx);
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (bal == 0) continue;
+    if (pass) {
+      const int pos = count + __popc(bal & ((1u << lane) - 1));
+      qkey[warp][pos] = key;
+      qidx[warp][pos] = j;
+    }
+    count += __popc(bal);
+    __syncwarp();
+    if (count >= 32) {
+      T ckey = qkey[warp][lane];
+      int cidx = qidx[warp][lane];
+      __syncwarp();
+      // shift the tail of the queue down
+      if (lane + 32 < count) {
+        T tk = qkey[warp][lane + 32]; int ti = qidx[warp][lane + 32];
+        qkey[warp][lane] = tk; qidx[warp][lane] = ti;
+      }
+      count -= 32;
+      __syncwarp();
+      warp_merge<T>(bkey, bidx, ckey, cidx, lane);
+      thr_key = shfl_idx_t<T>(bkey, a.k - 1);
+      thr_idx = __shfl_sync(0xffffffffu, bidx, a.k - 1);
+    }
+  }
+  if (count > 0) {
+    T ckey = lane < count ? qkey[warp][lane] : INF;
+    int cidx = lane < count ? qidx[warp][lane] : IMAX;
+    warp_merge<T>(bkey, bidx, ckey, cidx, lane);
+  }
+  if (lane < a.k) {
+    const size_t o = (size_t)row * a.k + lane;
+    a.out_idx[o] = bidx;
+    if (a.out_ok) a.out_ok[o] = bkey <= a.valid_radius ? 1 : 0;
+  }
+}
+
+// k > 32: block-wide bitonic sort of all N candidates in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+knn_block_sort_kernel(const SelArgs<T> a, int Npad) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  T* keys = reinterpret_cast<T*>(sel_smem);
+  int* idxs = reinterpret_cast<int*>(keys + Npad);
+  const int row = blockIdx.x;
+  const int b = row / a.N, i = row % a.N;
+  const T* xi = a.coors + (size_t)row * a.C;
+  const bool mask_i = a.mask ? a.mask[row] != 0 : true;
+  for (int j = threadIdx.x; j < Npad; j += blockDim.x) {
+    keys[j] = j < a.N ? rank_of<T>(a, b, i, j, xi, mask_i) : T(INFINITY);
+    idxs[j] = j < a.N ? j : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int size = 2; size <= Npad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < Npad / 2; t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));     // index with the `stride` bit clear
+        const int hi = lo + stride;
+        const bool asc = (lo & size) == 0;
+        const bool hi_less = lex_less<T>(keys[hi], idxs[hi], keys[lo], idxs[lo]);
+        if (hi_less == asc) {
+          T tk = keys[lo]; keys[lo] = keys[hi]; keys[hi] = tk;
+          int ti = idxs[lo]; idxs[lo] = idxs[hi]; idxs[hi] = ti;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int s = threadIdx.x; s < a.k; s += blockDim.x) {
+    const size_t o = (size_t)row * a.k + s;
+    a.out_idx[o] = idxs[s];
+    if (a.out_ok) a.out_ok[o] = keys[s] <= a.valid_radius ? 1 : 0;
+  }
+}
+
+template <typename T>
+static int launch_select(int B, int N, int C, int k, const void* coors, const uint8_t* mask, const uint8_t* adj,
+                         int adj_batched, float valid_radius, int32_t* out_idx, uint8_t* out_ok, cudaStream_t st) {
+  SelArgs<T> a;
+  a.B = B; a.N = N; a.C = C; a.k = k;
+  a.coors = static_cast<const T*>(coors);
+  a.mask = mask; a.adj = adj; a.adj_batched = adj_batched;
+  a.valid_radius = (T)valid_radius;
+  a.out_idx = out_idx; a.out_ok = out_ok;
+  const int rows = B * N;
+  if (k <= 32) {
+    knn_warp_select_kernel<T><<<ceil_div(rows, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(a);
+  } else {
+    int Npad = 1;
+    while (Npad < N) Npad <<= 1;
+    const size_t smem = (size_t)Npad * (sizeof(T) + sizeof(int));
+    if (smem > 200 * 1024) return EGNN_ERR_UNSUPPORTED;     // N too large for the k>32 path
+    EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_block_sort_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_block_sort_kernel<T><<<rows, 256, smem, st>>>(a, Npad);
+  }
+  EGNN_LAUNCH_CHECK();
+  return EGNN_OK;
+}
+
+int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
+                        const uint8_t* adj, int adj_batched, float valid_radius, int32_t* out_idx,
+                        uint8_t* out_ok, cudaStream_t st) {
+  if (!coors || !out_idx) return EGNN_ERR_NULL;
+  if (B <= 0 || N <= 0 || C <= 0 || C > 8 || k <= 0 || k > N) return EGNN_ERR_SHAPE;
+  if (dtype == EGNN_DTYPE_F64)
+    return launch_select<double>(B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx, out_ok, st);
+  return launch_select<float>(B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx, out_ok, st);
+}
+
+}  // namespace egnn
+
+extern "C" int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, int32_t k, const void* coors,
+                               const uint8_t* mask, const uint8_t* adj, int32_t adj_batched,
+                               float valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream) {
+  return egnn::knn_select_dispatch(dtype, B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx,
+                                   out_ok, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's module interface for the EGNN forward hot path.
+
+`EGNN` and `EGNN_Network` keep the constructor arguments, forward signatures, return values and
+state-dict keys of lucidrains/egnn-pytorch (reference egnn_pytorch/egnn_pytorch.py:148-341 and
+:343-454), so a reference `state_dict()` loads unchanged -- but `forward` does not execute any
+PyTorch arithmetic for the edge step: it packs a POD descriptor and calls the hand-written
+sm_100a kernels of libegnn_b200.so through the C ABI (include/egnn_b200.h) on the current CUDA
+stream.  PyTorch is used for parameter storage, device memory and streams only.
+
+There is no CPU compute path.  CPU tensors (the reference's own tests pass CPU float64) are
+staged to the current CUDA device and the results copied back -- a transport convenience.
+
+Element type -> kernel family
+    float64 parameters  -> fp64 SIMT kernels      (parity with the fp64 oracle to ~1e-12)
+    float32 parameters  -> fp32 SIMT kernels      ("accurate": the stated-fp32-tolerance path)
+    bfloat16 parameters -> tcgen05 bf16 tensor-core kernels with fp32 accumulation ("fast");
+                           option combinations the tensor-core kernels do not cover run on the
+                           fp32 SIMT kernels instead (still on the GPU; see `last_path`).
+`precision='fast'` / `'accurate'` overrides the choice for fp32/bf16 parameters.
+
+Forward only in this round: outputs carry no autograd graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import _native as nat
+
+__all__ = ["EGNN", "EGNN_Network", "CoorsNorm", "GlobalLinearAttention"]
+
+
+def exists(v):
+    return v is not None
+
+
+# ----------------------------------------------------------------------------- runtime helpers
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) scratch arena, grown on demand; the library never allocates."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _compute_device(t: torch.Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("egnn_pytorch_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+_KERNEL_DTYPE = {torch.float32: nat.DTYPE_F32, torch.float64: nat.DTYPE_F64, torch.bfloat16: nat.DTYPE_BF16}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ----------------------------------------------------------------------------- small modules
+
+
+class CoorsNorm(nn.Module):
+    """Parameter holder for `coors_norm.scale` (reference egnn_pytorch.py:67-77); the
+    normalisation x / max(|x|, eps) * scale itself runs inside the fused edge kernel."""
+
+    def __init__(self, eps=1e-8, scale_init=1.0):
+        super().__init__()
+        self.eps = eps
+        self.scale = nn.Parameter(torch.full((1,), float(scale_init)))
+
+
+def _mlp(d_in, d_hidden, d_out, dropout, final_act=False):
+    """Linear -> (Dropout|Identity) -> SiLU -> Linear [-> SiLU]; the Sequential indices (0 and 3)
+    are part of the state-dict contract (reference :178-184, :196-201, :203-208)."""
+    mods = [nn.Linear(d_in, d_hidden), nn.Dropout(dropout) if dropout > 0 else nn.Identity(), nn.SiLU(),
+            nn.Linear(d_hidden, d_out)]
+    if final_act:
+        mods.append(nn.SiLU())
+    return nn.Sequential(*mods)
+
+
+# ----------------------------------------------------------------------------- the layer
+
+
+class EGNN(nn.Module):
+    """Drop-in for `egnn_pytorch.EGNN` (reference egnn_pytorch.py:148-341)."""
+
+    def __init__(self, dim, edge_dim=0, m_dim=16, fourier_features=0, num_nearest_neighbors=0, dropout=0.0,
+                 init_eps=1e-3, norm_feats=False, norm_coors=False, norm_coors_scale_init=1e-2,
+                 update_feats=True, update_coors=True, only_sparse_neighbors=False, valid_radius=float("inf"),
+                 m_pool_method="sum", soft_edges=False, coor_weights_clamp_value=None, precision="auto"):
+        super().__init__()
+        assert m_pool_method in {"sum", "mean"}, "pool method must be either sum or mean"
+        assert update_feats or update_coors, "you must update either features, coordinates, or both"
+        assert precision in {"auto", "accurate", "fast"}
+        self.dim, self.edge_dim, self.m_dim = dim, edge_dim, m_dim
+        self.fourier_features = fourier_features
+        edge_input_dim = fourier_features * 2 + dim * 2 + edge_dim + 1
+        self.edge_mlp = _mlp(edge_input_dim, edge_input_dim * 2, m_dim, dropout, final_act=True)
+        self.edge_gate = nn.Sequential(nn.Linear(m_dim, 1), nn.Sigmoid()) if soft_edges else None
+        self.node_norm = nn.LayerNorm(dim) if norm_feats else nn.Identity()
+        self.coors_norm = CoorsNorm(scale_init=norm_coors_scale_init) if norm_coors else nn.Identity()
+        self.m_pool_method = m_pool_method
+        self.node_mlp = _mlp(dim + m_dim, dim * 2, dim, dropout) if update_feats else None
+        self.coors_mlp = _mlp(m_dim, m_dim * 4, 1, dropout) if update_coors else None
+        self.num_nearest_neighbors = num_nearest_neighbors
+        self.only_sparse_neighbors = only_sparse_neighbors
+        self.valid_radius = valid_radius
+        self.coor_weights_clamp_value = coor_weights_clamp_value
+        self.dropout_p = dropout
+        self.init_eps = init_eps
+        self.precision = precision
+        self.last_path = None          # 'fp64-simt' | 'fp32-simt' | 'bf16-tcgen05' of the last call
+        self._stage = {}
+        self.apply(self._init)
+
+    def _init(self, module):
+        if type(module) is nn.Linear:
+            nn.init.normal_(module.weight, std=self.init_eps)      # reference :219-222
+
+    # -------------------------------------------------------------- parameter staging
+    def _state_fields(self):
+        out = {}
+        for key, p in self.named_parameters():
+            f = nat.STATE_KEY_TO_FIELD.get(key)
+            if f is not None:
+                out[f] = p
+        return out
+
+    def _staged(self, device, dtype):
+        fields = self._state_fields()
+        sig = tuple((n, p.data_ptr(), p._version, p.dtype, str(p.device)) for n, p in fields.items())
+        key = (str(device), dtype)
+        st = self._stage.get(key)
+        if st is None or st["sig"] != sig:
+            with torch.no_grad():
+                tensors = {n: p.detach().to(device=device, dtype=dtype).contiguous() for n, p in fields.items()}
+            st = dict(sig=sig, tensors=tensors, packed={})
+            self._stage[key] = st
+        return st
+
+    def _flags(self):
+        fl = 0
+        if isinstance(self.node_norm, nn.LayerNorm): fl |= nat.FLAG_NORM_FEATS
+        if isinstance(self.coors_norm, CoorsNorm): fl |= nat.FLAG_NORM_COORS
+        if self.node_mlp is not None: fl |= nat.FLAG_UPDATE_FEATS
+        if self.coors_mlp is not None: fl |= nat.FLAG_UPDATE_COORS
+        if self.edge_gate is not None: fl |= nat.FLAG_SOFT_EDGES
+        if self.m_pool_method == "mean": fl |= nat.FLAG_POOL_MEAN
+        if self.coor_weights_clamp_value is not None: fl |= nat.FLAG_CLAMP
+        return fl
+
+    def _kernel_dtype(self):
+        pd = self.edge_mlp[0].weight.dtype
+        if pd == torch.float64:
+            return torch.float64
+        prec = os.environ.get("EGNN_B200_PRECISION", self.precision)
+        if prec == "fast" or (prec == "auto" and pd == torch.bfloat16):
+            return torch.bfloat16
+        return torch.float32
+
+    # -------------------------------------------------------------- forward
+    @torch.no_grad()
+    def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, *, _edge_labels=None, _label_emb=None,
+                _k_hint=None, _rows=None):
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError("dropout in training mode is outside this forward-only build")
+        lib = nat.load()
+        dev = _compute_device(feats)
+        b, n, d = feats.shape
+        assert d == self.dim, f"feature width {d} != dim {self.dim}"
+        c = coors.shape[-1]
+        kdt = self._kernel_dtype()
+        label_dim = 0 if _label_emb is None else _label_emb.shape[1]
+        cont_edge_dim = self.edge_dim - label_dim
+        assert (edges is None) == (cont_edge_dim == 0), "edges must be given iff edge_dim > 0"
+
+        use_nearest = self.num_nearest_neighbors > 0 or self.only_sparse_neighbors          # reference :230
+        adj_u8 = None
+        k = 0
+        flags = self._flags()
+        if use_nearest:
+            k = self.num_nearest_neighbors
+            if exists(adj_mat):
+                adj_u8 = adj_mat.to(device=dev).ne(0).to(torch.uint8).contiguous()
+                if adj_u8.dim() == 3:
+                    flags |= nat.FLAG_ADJ_BATCHED
+                if self.only_sparse_neighbors:
+                    flags |= nat.FLAG_ONLY_SPARSE                                    # valid_radius := 0 (:250)
+                    # reference :249 -- one host sync, diagonal still counted
+                    k = int(_k_hint) if _k_hint is not None else int(adj_u8.sum(dim=-1, dtype=torch.int32).max().item())
+            if not (0 < k <= n):
+                raise RuntimeError(f"number of neighbours k={k} must satisfy 0 < k <= N={n} (torch.topk would raise)")
+
+        for attempt_dt in ([kdt, torch.float32] if kdt == torch.bfloat16 else [kdt]):
+            try:
+                return self._run(lib, dev, attempt_dt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
+                                 b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
+            except nat.EgnnNativeError as e:
+                if e.code == nat.ERR_UNSUPPORTED and attempt_dt == torch.bfloat16:
+                    continue        # tensor-core kernels do not cover this option set: fp32 SIMT kernels
+                raise
+
+    def _run(self, lib, dev, kdt, feats, coors, edges, mask, adj_u8, labels, label_emb, b, n, c, k, flags,
+             cont_edge_dim, label_dim, rows):
+        cdt = torch.float64 if kdt == torch.float64 else torch.float32
+        st = self._staged(dev, kdt)
+        T = dict(st["tensors"])
+        lab_w = None
+        if label_emb is not None:
+            lab_w = label_emb.detach().to(device=dev, dtype=kdt).contiguous()
+            T["label_emb"] = lab_w
+
+        desc = nat.LayerDesc(
+            abi_version=nat.ABI_VERSION, dtype=_KERNEL_DTYPE[kdt], B=b, N=n, C=c, dim=self.dim,
+            edge_dim=cont_edge_dim, label_dim=label_dim, num_labels=0 if label_emb is None else label_emb.shape[0],
+            m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
+            valid_radius=float(min(self.valid_radius, 3.0e38)),
+            clamp=float(self.coor_weights_clamp_value or 0.0),
+            row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1])
+        w = nat.LayerWeights(**{f: (T[f].data_ptr() if f in T else None) for f in nat.WEIGHT_FIELDS})
+
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            # packed parameters, cached until a parameter changes
+            pkey = (label_dim, 0 if lab_w is None else (label_emb.data_ptr(), label_emb._version))
+            packed = st["packed"].get(pkey)
+            if packed is None:
+                nb = C.c_size_t()
+                nat.check("egnn_layer_packed_bytes", lib.egnn_layer_packed_bytes(C.byref(desc), C.byref(nb)))
+                packed = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                nat.check("egnn_layer_pack_weights",
+                          lib.egnn_layer_pack_weights(C.byref(desc), C.byref(w), _ptr(packed), nb.value, stream))
+                st["packed"] = {pkey: packed}
+
+            f_in = feats.detach().to(device=dev, dtype=kdt, non_blocking=True).contiguous()
+            x_in = coors.detach().to(device=dev, dtype=cdt, non_blocking=True).contiguous()
+            e_in = None if edges is None else edges.detach().to(device=dev, dtype=kdt, non_blocking=True).contiguous()
+            m_in = None if mask is None else mask.to(device=dev, non_blocking=True).ne(0).to(torch.uint8).contiguous()
+            l_in = None if labels is None else labels.to(device=dev, dtype=torch.uint8).contiguous()
+            f_out = torch.empty_like(f_in)
+            x_out = torch.empty_like(x_in)
+            if rows is not None:       # rows outside the range keep the input values
+                f_out.copy_(f_in)
+                x_out.copy_(x_in)
+            io = nat.LayerIO(feats=f_in.data_ptr(), coors=x_in.data_ptr(), edges=None if e_in is None else e_in.data_ptr(),
+                             edge_labels=None if l_in is None else l_in.data_ptr(),
+                             mask=None if m_in is None else m_in.data_ptr(),
+                             adj=None if adj_u8 is None else adj_u8.data_ptr(),
+                             feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr())
+            nb = C.c_size_t()
+            nat.check("egnn_layer_workspace_bytes", lib.egnn_layer_workspace_bytes(C.byref(desc), C.byref(nb)))
+            ws = _workspace(dev, nb.value)
+            nat.check("egnn_layer_forward",
+                      lib.egnn_layer_forward(C.byref(desc), C.byref(w), _ptr(packed), C.byref(io), _ptr(ws),
+                                             ws.numel(), stream))
+        self.last_path = {torch.float64: "fp64-simt", torch.float32: "fp32-simt", torch.bfloat16: "bf16-tcgen05"}[kdt]
+        return (f_out.to(device=feats.device, dtype=feats.dtype), x_out.to(device=coors.device, dtype=coors.dtype))
+
+
+# ----------------------------------------------------------------------------- global attention (PyTorch glue)
+
+
+class _Attention(nn.Module):
+    """Multi-head softmax attention used by GlobalLinearAttention (reference :81-110).  Outside
+    the hot path: stock PyTorch SDPA, kept for API completeness."""
+
+    def __init__(self, dim, heads=8, dim_head=64):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads = heads
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_kv = nn.Linear(dim, inner * 2, bias=False)
+        self.to_out = nn.Linear(inner, dim)
+
+    def forward(self, x, context, mask=None):
+        h = self.heads
+        q = self.to_q(x)
+        k, v = self.to_kv(context).chunk(2, dim=-1)
+        split = lambda t: t.unflatten(-1, (h, -1)).transpose(1, 2)
+        attn_mask = None if mask is None else mask[:, None, None, :].to(torch.bool)
+        out = F.scaled_dot_product_attention(split(q), split(k), split(v), attn_mask=attn_mask)
+        return self.to_out(out.transpose(1, 2).flatten(-2))
+
+
+class GlobalLinearAttention(nn.Module):
+    """Induced-set attention between the nodes and a few global tokens (reference :112-144)."""
+
+    def __init__(self, *, dim, heads=8, dim_head=64):
+        super().__init__()
+        self.norm_seq = nn.LayerNorm(dim)
+        self.norm_queries = nn.LayerNorm(dim)
+        self.attn1 = _Attention(dim, heads, dim_head)
+        self.attn2 = _Attention(dim, heads, dim_head)
+        self.ff = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, dim * 4), nn.GELU(), nn.Linear(dim * 4, dim))
+
+    def forward(self, x, queries, mask=None):
+        nx, nq = self.norm_seq(x), self.norm_queries(queries)
+        induced = self.attn1(nq, nx, mask=mask)
+        x = self.attn2(nx, induced) + x
+        queries = induced + queries
+        return self.ff(x) + x, queries
+
+
+# ----------------------------------------------------------------------------- the network
+
+
+class EGNN_Network(nn.Module):
+    """Drop-in for `egnn_pytorch.EGNN_Network` (reference egnn_pytorch.py:343-454).
+
+    Differences in mechanism, not in results: the N-th degree adjacency is expanded on bit-packed
+    rows by `egnn_adj_expand` instead of dense `A @ A` (:425), and the adjacency-degree embedding
+    is never materialised as a [B,N,N,adj_dim] tensor (:430-432) -- layers receive the uint8 degree
+    labels and fold `adj_emb.weight` into a [num_degrees+1, H] table."""
+
+    def __init__(self, *, depth, dim, num_tokens=None, num_edge_tokens=None, num_positions=None, edge_dim=0,
+                 num_adj_degrees=None, adj_dim=0, global_linear_attn_every=0, global_linear_attn_heads=8,
+                 global_linear_attn_dim_head=64, num_global_tokens=4, **kwargs):
+        super().__init__()
+        assert not (exists(num_adj_degrees) and num_adj_degrees < 1), "make sure adjacent degrees is greater than 1"
+        self.num_positions = num_positions
+        self.token_emb = nn.Embedding(num_tokens, dim) if exists(num_tokens) else None
+        self.pos_emb = nn.Embedding(num_positions, dim) if exists(num_positions) else None
+        self.edge_emb = nn.Embedding(num_edge_tokens, edge_dim) if exists(num_edge_tokens) else None
+        self.has_edges = edge_dim > 0
+        self.num_adj_degrees = num_adj_degrees
+        self.adj_emb = nn.Embedding(num_adj_degrees + 1, adj_dim) if exists(num_adj_degrees) and adj_dim > 0 else None
+        edge_dim = edge_dim if self.has_edges else 0
+        adj_dim = adj_dim if exists(num_adj_degrees) else 0
+        has_global_attn = global_linear_attn_every > 0
+        self.global_tokens = nn.Parameter(torch.randn(num_global_tokens, dim)) if has_global_attn else None
+        self.layers = nn.ModuleList()
+        for ind in range(depth):
+            is_global = has_global_attn and (ind % global_linear_attn_every) == 0
+            self.layers.append(nn.ModuleList([
+                GlobalLinearAttention(dim=dim, heads=global_linear_attn_heads,
+                                      dim_head=global_linear_attn_dim_head) if is_global else None,
+                EGNN(dim=dim, edge_dim=edge_dim + adj_dim, norm_feats=True, **kwargs),
+            ]))
+
+    @torch.no_grad()
+    def forward(self, feats, coors, adj_mat=None, edges=None, mask=None, return_coor_changes=False):
+        lib = nat.load()
+        out_dev = coors.device
+        dev = _compute_device(coors)
+        b = feats.shape[0]
+        feats, coors = feats.to(dev), coors.to(dev)
+        adj_mat = None if adj_mat is None else adj_mat.to(dev)
+        edges = None if edges is None else edges.to(dev)
+        mask = None if mask is None else mask.to(dev)
+
+        def staged(emb):
+            return emb.weight if emb.weight.device == dev else emb.weight.to(dev)
+
+        if exists(self.token_emb):
+            feats = F.embedding(feats, staged(self.token_emb))                       # reference :401-402
+        if exists(self.pos_emb):
+            n = feats.shape[1]
+            assert n <= self.num_positions, \
+                f"given sequence length {n} must be less than the number of positions {self.num_positions} set at init"
+            feats = feats + staged(self.pos_emb)[:n].unsqueeze(0)                    # :404-408
+        if exists(edges) and exists(self.edge_emb):
+            edges = F.embedding(edges, staged(self.edge_emb))                        # :410-411
+
+        labels = label_emb = k_hint = None
+        if exists(self.num_adj_degrees):
+            assert exists(adj_mat), "adjacency matrix must be passed in (keyword argument adj_mat)"
+            n = adj_mat.shape[-1]
+            adj_in = adj_mat.ne(0).to(torch.uint8).contiguous()
+            adj_out = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
+            lab = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
+            max_sum = torch.zeros(1, dtype=torch.int32, device=dev)
+            nb = C.c_size_t()
+            nat.check("egnn_adj_workspace_bytes", lib.egnn_adj_workspace_bytes(b, n, C.byref(nb)))
+            with torch.cuda.device(dev):
+                ws = _workspace(dev, nb.value)
+                nat.check("egnn_adj_expand", lib.egnn_adj_expand(
+                    b, n, self.num_adj_degrees, _ptr(adj_in), 1 if adj_in.dim() == 3 else 0, _ptr(adj_out), _ptr(lab),
+                    _ptr(max_sum), _ptr(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            adj_mat = adj_out                                                        # layers see the expanded matrix (:428, :448)
+            if exists(self.adj_emb):
+                labels, label_emb = lab, self.adj_emb.weight
+            if self.layers[0][1].only_sparse_neighbors:
+                k_hint = int(max_sum.item())                                         # the reference's sync at :249
+
+        global_tokens = None
+        if exists(self.global_tokens):
+            global_tokens = self.global_tokens.to(dev).unsqueeze(0).expand(b, -1, -1)
+
+        coor_changes = [coors]
+        for global_attn, egnn in self.layers:
+            if exists(global_attn):
+                global_attn = global_attn.to(dev)
+                feats, global_tokens = global_attn(feats, global_tokens, mask=mask)
+            feats, coors = egnn(feats, coors, edges, mask, adj_mat, _edge_labels=labels, _label_emb=label_emb,
+                                _k_hint=k_hint)
+            coor_changes.append(coors)
+
+        feats, coors = feats.to(out_dev), coors.to(out_dev)
+        if return_coor_changes:
+            return feats, coors, [c.to(out_dev) for c in coor_changes]
+        return feats, coors
