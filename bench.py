@@ -145,14 +145,24 @@ def equivariance_error(mod, feats, coors, dtype, device):
 
 
 # ----------------------------------------------------------------------------- CPU baseline (oracle port)
+_CPU_JOB = {}
+
+
+def _cpu_job(span):
+    from oracle import egnn_oracle as O
+    j = _CPU_JOB
+    O.egnn_layer_forward(j["params"], j["cfg"], j["feats"], j["coors"], dtype=np.float32, row_chunk=j["block"], rows=span)
+    return span[1] - span[0]
+
+
 def cpu_baseline_sample(name, target_seconds=12.0, seed=0):
     """Time the oracle (numpy float32) on a bounded sample of the workload: `rows` i-rows of ONE
-    graph against all N neighbours.  The rows are split over one worker thread per host core
-    (numpy releases the GIL inside BLAS and ufuncs; BLAS is pinned to 1 thread per worker), so
-    both the Linear-1 GEMM and the elementwise SiLU use every core."""
+    graph against all N neighbours, the rows split over one forked worker PROCESS per host core
+    (single-threaded BLAS in each), so both the Linear-1 GEMM and the elementwise SiLU use every
+    core.  Must run in a process that has not initialised CUDA (bench.py's GPU arm calls it through
+    `python bench.py --impl cpu-sample`)."""
+    import multiprocessing as mp
     import cases
-    from concurrent.futures import ThreadPoolExecutor
-    from oracle import egnn_oracle as O
     try:
         from threadpoolctl import threadpool_limits
     except Exception:                       # pragma: no cover
@@ -163,26 +173,39 @@ def cpu_baseline_sample(name, target_seconds=12.0, seed=0):
     spec = dict(kind="layer", cfg=w["cfg"], B=1, N=w["N"], C=w["C"], seed=seed)
     case = cases.build_case(spec)
     ins = case["inputs"]
-    params32 = {k: np.asarray(v, np.float32) for k, v in case["params"].items()}
-    f32, x32 = ins["feats"].astype(np.float32), ins["coors"].astype(np.float32)
     block = 8
+    _CPU_JOB.update(params={k: np.asarray(v, np.float32) for k, v in case["params"].items()}, cfg=case["cfg"],
+                    feats=ins["feats"].astype(np.float32), coors=ins["coors"].astype(np.float32), block=block)
+    with threadpool_limits(limits=1):
+        with mp.get_context("fork").Pool(cores) as pool:
+            def run(rows):
+                spans = [(a, min(a + block, rows)) for a in range(0, rows, block)]
+                t0 = time.perf_counter()
+                pool.map(_cpu_job, spans, chunksize=1)
+                return time.perf_counter() - t0
+            probe = min(block * cores, w["N"])
+            run(probe)                               # warm-up (page faults, BLAS init in the workers)
+            dt = run(probe)
+            reps = int(max(1, min(64, target_seconds / max(dt, 1e-3))))
+            rows_list = [min(w["N"], probe)] * reps
+            if probe < w["N"]:
+                rows = int(min(w["N"], max(probe, probe * target_seconds / max(dt, 1e-3))))
+                rows_list = [max(block, rows // block * block)]
+            t = sum(run(r) for r in rows_list)
+    pairs = sum(rows_list) * w["N"]
+    return dict(value=pairs / t, unit="pairs/s", cores=cores, kind="port",
+                sample=f"{len(rows_list)} x {rows_list[0]} of {w['N']} i-rows of one graph x all {w['N']} neighbours "
+                       f"({pairs} pairs, {t:.1f} s), numpy float32 oracle, {cores} worker processes"), pairs, t
 
-    def run(rows):
-        spans = [(a, min(a + block, rows)) for a in range(0, rows, block)]
-        job = lambda sp: O.egnn_layer_forward(params32, case["cfg"], f32, x32, dtype=np.float32, row_chunk=block, rows=sp)
-        with threadpool_limits(limits=1), ThreadPoolExecutor(max_workers=cores) as ex:
-            list(ex.map(job, spans))
 
-    probe = min(block * cores, w["N"])
-    run(probe)                                   # warm-up (threads, page faults)
-    t0 = time.perf_counter(); run(probe); dt = time.perf_counter() - t0
-    rows = int(min(w["N"], max(probe, probe * target_seconds / max(dt, 1e-4))))
-    rows = max(block, rows // block * block)
-    t0 = time.perf_counter(); run(rows); dt = time.perf_counter() - t0
-    pairs = rows * w["N"]
-    return dict(value=pairs / dt, unit="pairs/s", cores=cores, kind="port",
-                sample=f"{rows} of {w['N']} i-rows of one graph x all {w['N']} neighbours ({pairs} pairs, {dt:.1f} s), "
-                       f"numpy float32 oracle, {cores} worker threads"), pairs, dt
+def cpu_baseline_subprocess(name):
+    """Run the sample in a fresh interpreter (no CUDA context, fork-safe)."""
+    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--workload", name],
+                         capture_output=True, text=True, timeout=900)
+    for line in reversed(res.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    return dict(value=None, unit="pairs/s", cores=os.cpu_count(), kind="port", sample="failed: " + res.stderr[-300:])
 
 
 # ----------------------------------------------------------------------------- arms
@@ -311,7 +334,7 @@ def arm_ours(args):
         gpu_launches=int(launches.value), clocks=clocks, roofline=roofline,
         equivariance_err=equivariance_error(mod, feats, coors, dtype, dev))
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"], _, _ = cpu_baseline_sample(args.workload)
+        out["cpu_baseline"] = cpu_baseline_subprocess(args.workload)
     print(json.dumps(out))
 
 
@@ -379,11 +402,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager", "cpu-sample"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.impl == "cpu-sample":
+        print(json.dumps(cpu_baseline_sample(args.workload)[0]))
+        return
     {"ours": arm_ours, "reference": arm_reference, "eager": arm_eager}[args.impl](args)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist

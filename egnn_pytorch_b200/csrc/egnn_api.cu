@@ -308,6 +308,11 @@ extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLaye
   return rc;
 }
 
+extern "C" int egnn_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, const void* W, const float* bias,
+                              float scale, int32_t act, void* out, int32_t out_f32, void* stream) {
+  return debug_gemm_bf16(M, N, K, A, W, bias, scale, act, out, out_f32, static_cast<cudaStream_t>(stream));
+}
+
 // ---- diagnostics (see profile.h): per-stage CUDA-event timing on the launch stream ----------
 extern "C" int egnn_profile_enable(int on) {
   Profiler& p = Profiler::get();

@@ -1,0 +1,312 @@
+// The fused edge step on 5th-gen tensor cores (dense all-pairs, bf16 operands, fp32 accumulation).
+//
+// Reference semantics: egnn_pytorch.py:232-233 (x_i - x_j, squared distance), :282-287 (edge MLP on
+// [h_i | h_j | d]), :289-290 (gate), :292-333 (masks, coors MLP, clamp, both sums over j).
+//
+// Per pair (i, j) the split form needs  hidden[c] = SiLU(A_i[c] + B_j[c] + wd[c] d_ij), c < H, and
+// m_pre = hidden . W2^T  (H -> 16).  One CTA owns TI = 8 query rows i and walks all j in blocks of 256:
+//   * 2 compute warpgroups (128 threads each); a thread owns one neighbour j of the block and produces,
+//     for each of the 8 rows i and each 64-wide hidden chunk, the 64 bf16 hidden values of pair (i, j)
+//     in registers (fp32 math, one MUFU.TANH per value) and stores them with tcgen05.st into a TMEM
+//     slot laid out as the A operand (lane = pair, 32 columns = 64 bf16) -- the O(N^2 H) hidden tensor
+//     lives only in TMEM, 8 KB at a time;
+//   * 1 MMA warp per warpgroup: tcgen05.mma.kind::f16 (M=128 pairs, N=16, K=16) x4 per chunk with A from
+//     TMEM and B = the W2 slab from shared memory, accumulating m_pre[i] (128 x 16 fp32) in TMEM across
+//     all chunks; slot hand-over through full/empty mbarriers (tcgen05.commit);
+//   * after the last chunk the same threads read their pair's 16 accumulators back (tcgen05.ld), apply
+//     SiLU / gate / coors MLP / mask / clamp in fp32 and reduce over j with warp shuffles; per-row sums
+//     sum_j m_ij and sum_j w_ij (x_i - x_j) are kept in shared memory and written once per row.
+// W2 (packed in UMMA core-matrix order), the 8 A_i rows and wd are staged once per CTA with TMA bulk
+// copies (cp.async.bulk -> UBLKCP) onto an mbarrier.
+#pragma once
+
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace egnn {
+
+constexpr int TP_TI = 8;          // query rows per CTA
+constexpr int TP_KC = 64;         // hidden channels per chunk (= 32 TMEM columns, 4 MMAs)
+constexpr int TP_SLOTS = 4;       // A-operand slots per warpgroup
+constexpr int TP_WG = 2;          // compute warpgroups
+constexpr int TP_THREADS = TP_WG * 128 + TP_WG * 32;
+constexpr int TP_JB = TP_WG * 128;   // neighbours per block
+constexpr int TP_EPI_FLOATS = 64 * 16 + 64 + 64 + 16 + 16 + 4;   // W3 | b3 | w4 | b2 | gate_w | gate_b, b4, scale, 0
+
+struct TcPairArgs {
+  int B, N, Hp, ldn, dim;          // ldn: row stride of node_in (bf16 elements)
+  uint32_t flags; int has_mask; float clamp; uint32_t variant;
+  const float* Atab;               // [M][Hp]  0.5 (h W1_i^T + b1)
+  const __nv_bfloat16* Btab;       // [M][Hp]  0.5 h W1_j^T
+  const float* wdh;                // [Hp]     0.5 W1[:, 2dim]
+  const __nv_bfloat16* w2p;        // [Hp/16][2][2][8][8]  W2 in core-matrix order
+  const float* epi;                // TP_EPI_FLOATS
+  const float* coors;              // [B][N][3]
+  const uint8_t* mask;             // [B][N] | null
+  __nv_bfloat16* m_out;            // node_in + dim (stride ldn) | null
+  float* coors_out;                // [B][N][3] | null
+};
+
+inline size_t tc_pair_smem_bytes(int Hp) {
+  size_t n = 0;
+  n += (size_t)Hp * 32;                       // W2 slabs
+  n += (size_t)TP_TI * Hp * 4;                // A rows (fp32)
+  n += (size_t)Hp * 4;                        // wd
+  n += (size_t)TP_EPI_FLOATS * 4;             // epilogue constants
+  n += (size_t)TP_WG * 4 * TP_TI * 20 * 4;    // per-warp partial sums
+  n += (size_t)TP_TI * 4 * 4 + 64;            // x_i, mask_i
+  n += (size_t)TP_TI * TP_JB * 4;             // d_ij of the current j-block (per thread, per row)
+  n += 32 * 8;                                // mbarriers
+  return n + 1024;                            // alignment slack
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs a) {
+  extern __shared__ __align__(1024) unsigned char tp_smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tp_smem_raw) + 1023) & ~uintptr_t(1023));
+  const int Hp = a.Hp, N = a.N;
+  unsigned char* w2s = sm;                                                    // Hp*32 bytes
+  float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [TI][Hp]
+  float* wds = As + (size_t)TP_TI * Hp;                                       // [Hp]
+  float* epi = wds + Hp;                                                      // constants
+  float* part = epi + TP_EPI_FLOATS;                                          // [8 warps][TI][20]
+  float* xis = part + TP_WG * 4 * TP_TI * 20;                                 // [TI][4]
+  uint32_t* mki = reinterpret_cast<uint32_t*>(xis + TP_TI * 4);               // [TI] (+ tmem ptr at [15])
+  float* dsm = reinterpret_cast<float*>(mki + 16);                            // [TI][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + TP_TI * TP_JB);
+  uint64_t* full = bars;                       // [WG][SLOTS]
+  uint64_t* empty = bars + TP_WG * TP_SLOTS;   // [WG][SLOTS]
+  uint64_t* accdone = empty + TP_WG * TP_SLOTS;  // [WG]
+  uint64_t* ldbar = accdone + TP_WG;           // staging barrier
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i0 = blockIdx.x * TP_TI;
+  const int rows_valid = min(TP_TI, N - i0);
+  const int nchunks = Hp / TP_KC;
+  const int njb = (N + TP_JB - 1) / TP_JB;
+  const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
+
+  // ---------------- setup
+  if (tid == 0) {
+    for (int x = 0; x < TP_WG * TP_SLOTS; ++x) { tc::mbar_init(&full[x], 128); tc::mbar_init(&empty[x], 1); }
+    for (int x = 0; x < TP_WG; ++x) tc::mbar_init(&accdone[x], 1);
+    tc::mbar_init(ldbar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == TP_WG * 4) tc::tmem_alloc<512>(&mki[15]);
+  for (int x = tid; x < TP_EPI_FLOATS; x += TP_THREADS) epi[x] = a.epi[x];
+  for (int x = tid; x < TP_WG * 4 * TP_TI * 20; x += TP_THREADS) part[x] = 0.f;
+  if (tid < TP_TI) {
+    const bool v = tid < rows_valid;
+    const size_t node = (size_t)b * N + (v ? i0 + tid : i0);
+    xis[tid * 4 + 0] = a.coors[node * 3 + 0]; xis[tid * 4 + 1] = a.coors[node * 3 + 1]; xis[tid * 4 + 2] = a.coors[node * 3 + 2];
+    xis[tid * 4 + 3] = 0.f;
+    mki[tid] = v && (a.has_mask ? a.mask[node] != 0 : true);
+  }
+  // rows beyond the graph: zero A (their pairs are discarded anyway, keep them finite)
+  for (int x = tid + rows_valid * Hp; x < TP_TI * Hp; x += TP_THREADS) As[x] = 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = mki[15];
+
+  if (tid == 0) {
+    // TMA bulk staging: W2 slabs, the A_i rows of this CTA (contiguous in the table), wd
+    const uint32_t w2_bytes = (uint32_t)Hp * 32, as_bytes = (uint32_t)rows_valid * Hp * 4, wd_bytes = (uint32_t)Hp * 4;
+    tc::mbar_arrive_expect_tx(ldbar, w2_bytes + as_bytes + wd_bytes);
+    auto bulk = [&](uint32_t dst, const unsigned char* src, uint32_t bytes) {
+      for (uint32_t o = 0; o < bytes; o += 16384) tc::tma_bulk_g2s(dst + o, src + o, min(16384u, bytes - o), ldbar);
+    };
+    bulk(tc::smem_u32(w2s), reinterpret_cast<const unsigned char*>(a.w2p), w2_bytes);
+    bulk(tc::smem_u32(As), reinterpret_cast<const unsigned char*>(a.Atab + ((size_t)b * N + i0) * Hp), as_bytes);
+    bulk(tc::smem_u32(wds), reinterpret_cast<const unsigned char*>(a.wdh), wd_bytes);
+  }
+
+  if (warp < TP_WG * 4) {
+    // =========================================================== compute warpgroups
+    const int g = warp >> 2, wq = warp & 3, t128 = tid & 127;
+    const uint32_t tm_wg = tmem + g * 256 + ((uint32_t)(wq * 32) << 16);    // this warp's lane quadrant
+    float* mypart = part + (size_t)warp * TP_TI * 20;
+    tc::mbar_wait(ldbar, 0);
+    uint32_t n = 0;
+    for (int jb = 0; jb < njb; ++jb) {
+      const int j = jb * TP_JB + g * 128 + t128;
+      const bool jv = j < N;
+      const size_t nodej = (size_t)b * N + (jv ? j : N - 1);
+      const float xj0 = a.coors[nodej * 3 + 0], xj1 = a.coors[nodej * 3 + 1], xj2 = a.coors[nodej * 3 + 2];
+      const bool mask_j = jv && (a.has_mask ? a.mask[nodej] != 0 : true);
+      float* dmine = dsm + (g * 128 + t128);          // d_ij for i = 0..7 at stride 256 (private to this thread)
+#pragma unroll
+      for (int i = 0; i < TP_TI; ++i) {
+        const float r0 = xis[i * 4 + 0] - xj0, r1 = xis[i * 4 + 1] - xj1, r2 = xis[i * 4 + 2] - xj2;
+        dmine[i * TP_JB] = r0 * r0 + r1 * r1 + r2 * r2;
+      }
+      const uint4* Bp = reinterpret_cast<const uint4*>(a.Btab + nodej * Hp);
+      uint4 Bcur[8], Bnxt[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) Bcur[q] = __ldg(Bp + q);
+
+      for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) Bnxt[q] = __ldg(Bp + (c + 1) * 8 + q);
+        }
+        const float4* W4 = reinterpret_cast<const float4*>(wds + c * TP_KC);
+#pragma unroll 1
+        for (int i = 0; i < TP_TI; ++i, ++n) {
+          const uint32_t slot = n & (TP_SLOTS - 1);
+          tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n >> 2) & 1) ^ 1);
+          tc::tc_fence_after();
+          const float4* A4 = reinterpret_cast<const float4*>(As + (size_t)i * Hp + c * TP_KC);
+          const float di = dmine[i * TP_JB];
+          uint32_t hp[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint32_t bw[4] = {Bcur[q].x, Bcur[q].y, Bcur[q].z, Bcur[q].w};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 av = A4[q * 2 + h], wv = W4[q * 2 + h];
+              const uint32_t b01 = bw[h * 2], b23 = bw[h * 2 + 1];
+              const float y0 = fmaf(wv.x, di, av.x) + tc::bf16_lo(b01);
+              const float y1 = fmaf(wv.y, di, av.y) + tc::bf16_hi(b01);
+              const float y2 = fmaf(wv.z, di, av.z) + tc::bf16_lo(b23);
+              const float y3 = fmaf(wv.w, di, av.w) + tc::bf16_hi(b23);
+              const float h0 = tc::silu_half_arg(y0), h1 = tc::silu_half_arg(y1);
+              const float h2 = tc::silu_half_arg(y2), h3 = tc::silu_half_arg(y3);
+              if (a.variant & 2u) {
+                hp[q * 4 + h * 2] = tc::pack_bf16x2(h1, h0);
+                hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h3, h2);
+              } else {
+                hp[q * 4 + h * 2] = tc::pack_bf16x2(h0, h1);
+                hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h2, h3);
+              }
+            }
+          }
+          tc::tmem_st32(tm_wg + 128 + slot * 32, hp);
+          tc::tmem_wait_st();
+          tc::tc_fence_before();
+          tc::mbar_arrive(&full[g * TP_SLOTS + slot]);
+        }
+        if (c + 1 < nchunks) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) Bcur[q] = Bnxt[q];
+        }
+      }
+
+      // ---- epilogue of this j-block: accumulators back to the owning thread
+      tc::mbar_wait(&accdone[g], jb & 1);
+      tc::tc_fence_after();
+      const float* W3 = epi; const float* b3 = epi + 1024; const float* w4 = b3 + 64;
+      const float* b2 = w4 + 64; const float* gw = b2 + 16; const float* sc = gw + 16;   // sc: gate_b, b4, scale
+#pragma unroll 1
+      for (int i = 0; i < TP_TI; ++i) {
+        uint32_t r[16];
+        tc::tmem_ld16(tm_wg + i * 16, r);
+        tc::tmem_wait_ld();
+        float m[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) m[o] = tc::silu_half_arg(0.5f * (__uint_as_float(r[o]) + b2[o]));    // :183
+        if (a.flags & EGNN_FLAG_SOFT_EDGES) {                                                             // :289-290
+          float z = sc[0];
+#pragma unroll
+          for (int o = 0; o < 16; ++o) z = fmaf(gw[o], m[o], z);
+          const float gate = 0.5f + 0.5f * tc::tanh_fast(0.5f * z);
+#pragma unroll
+          for (int o = 0; o < 16; ++o) m[o] *= gate;
+        }
+        const bool pm = jv && (mki[i] != 0) && (a.has_mask ? mask_j : true);
+        float v[20];
+        float w = 0.f;
+        if (upd_coors) {                                                                                  // :302-315
+          w = sc[1];
+#pragma unroll 4
+          for (int u = 0; u < 64; ++u) {
+            const float4* w3 = reinterpret_cast<const float4*>(W3 + u * 16);
+            float tt = b3[u];
+#pragma unroll
+            for (int o4 = 0; o4 < 4; ++o4) {
+              const float4 ww = w3[o4];
+              tt = fmaf(ww.x, m[o4 * 4], tt); tt = fmaf(ww.y, m[o4 * 4 + 1], tt);
+              tt = fmaf(ww.z, m[o4 * 4 + 2], tt); tt = fmaf(ww.w, m[o4 * 4 + 3], tt);
+            }
+            w = fmaf(w4[u], tc::silu_half_arg(0.5f * tt), w);
+          }
+          if (!pm) w = 0.f;                                                                               // :309
+          if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);                          // :313
+          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dmine[i * TP_JB]), 1e-8f);                  // :74-77
+        }
+        v[16] = w * (xis[i * 4 + 0] - xj0); v[17] = w * (xis[i * 4 + 1] - xj1); v[18] = w * (xis[i * 4 + 2] - xj2);
+        v[19] = pm ? 1.f : 0.f;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) v[o] = pm ? m[o] : 0.f;                                              // :322
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+          for (int o = 0; o < 20; ++o) v[o] += __shfl_xor_sync(0xffffffffu, v[o], off);
+        if (lane == 0) {
+#pragma unroll
+          for (int o = 0; o < 20; ++o) mypart[i * 20 + o] += v[o];
+        }
+      }
+      tc::tc_fence_before();
+    }
+  } else {
+    // =========================================================== MMA issuers (one warp per warpgroup)
+    const int g = warp - TP_WG * 4;
+    if (lane == 0) {
+      constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
+      const uint32_t tm_g = tmem + g * 256;
+      const uint32_t w2a = tc::smem_u32(w2s);
+      const uint32_t lbo = (a.variant & 1u) ? 128u : 256u, sbo = (a.variant & 1u) ? 256u : 128u;
+      tc::mbar_wait(ldbar, 0);
+      uint32_t n = 0;
+      for (int jb = 0; jb < njb; ++jb) {
+        for (int c = 0; c < nchunks; ++c) {
+          for (int i = 0; i < TP_TI; ++i, ++n) {
+            const uint32_t slot = n & (TP_SLOTS - 1);
+            tc::mbar_wait(&full[g * TP_SLOTS + slot], (n >> 2) & 1);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < TP_KC / 16; ++kk) {
+              const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(c * 4 + kk) * 512, lbo, sbo);
+              tc::mma_ts(tm_g + i * 16, tm_g + 128 + slot * 32 + kk * 8, bd, IDESC, (c > 0 || kk > 0) ? 1u : 0u);
+            }
+            tc::mma_commit(&empty[g * TP_SLOTS + slot]);
+          }
+        }
+        tc::mma_commit(&accdone[g]);
+      }
+    }
+    __syncwarp();
+  }
+
+  // ---------------- per-row outputs
+  tc::tc_fence_before();
+  __syncthreads();
+  if (tid < TP_TI * 20) {
+    const int i = tid / 20, o = tid % 20;
+    if (i < rows_valid) {
+      float s = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < TP_WG * 4; ++wv) s += part[(size_t)wv * TP_TI * 20 + i * 20 + o];
+      const size_t node = (size_t)b * N + i0 + i;
+      if (o < 16) {
+        if (upd_feats) {
+          float inv = 1.f;
+          if (a.flags & EGNN_FLAG_POOL_MEAN) {
+            float cnt = 0.f;
+            for (int wv = 0; wv < TP_WG * 4; ++wv) cnt += part[(size_t)wv * TP_TI * 20 + i * 20 + 19];
+            inv = a.has_mask ? (cnt > 0.f ? 1.f / cnt : 0.f) : 1.f / (float)N;                            // :325-330
+          }
+          a.m_out[node * a.ldn + o] = __float2bfloat16(s * inv);
+        }
+      } else if (o < 19) {
+        if (upd_coors) a.coors_out[node * 3 + (o - 16)] = xis[i * 4 + (o - 16)] + s;                      // :315
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == TP_WG * 4) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace egnn

@@ -170,6 +170,12 @@ int egnn_adj_expand(int32_t B, int32_t N, int32_t num_degrees, const uint8_t* ad
                     int32_t adj_batched, uint8_t* adj_out, uint8_t* labels_out,
                     int32_t* max_row_sum, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The tcgen05 GEMM the bf16 path uses for its per-node contractions, exposed for unit tests:
+ * out[M,N] = act(scale * (A[M,K] W[N,K]^T + bias[N])), A/W bf16 row-major, K and N multiples of 8,
+ * act 0 = none / 1 = SiLU, out fp32 (out_f32 = 1) or bf16. */
+int egnn_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, const void* W, const float* bias,
+                   float scale, int32_t act, void* out, int32_t out_f32, void* stream);
+
 /* Diagnostics for benchmarks: when enabled, every egnn_layer_forward brackets its stages
  * (0 neighbour select, 1 per-node tables, 2 fused edge kernel, 3 node update) with CUDA events
  * on the launch stream and counts kernel launches.  egnn_profile_read synchronises those events

@@ -1,0 +1,105 @@
+"""The bf16 tensor-core path (tcgen05 GEMMs + the fused edge kernel) against the fp64 oracle.
+
+Inputs and parameters are rounded to bf16 first, so the comparison isolates the kernels' internal
+rounding (bf16 B' table, bf16 hidden operand, bf16 m_i / h1, tanh.approx) from input quantisation.
+Stated tolerance: max|err| <= 3e-2 * max|reference output| for feats and <= 3e-2 * max|coordinate
+update| + 1e-3 for coors; the reference itself run in bf16 deviates from its fp32 self by 1.6e-2 / 4.7e-2
+at default init and 0.10 / 0.52 with Xavier weights."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import util
+
+pytestmark = pytest.mark.gpu
+
+L = "layer"
+FAST_SPECS = {
+    "d64_n160":        dict(kind=L, cfg=dict(dim=64), B=2, N=160, seed=99, init="xavier"),
+    "d64_default":     dict(kind=L, cfg=dict(dim=64), B=1, N=257, seed=98),
+    "d128_mask":       dict(kind=L, cfg=dict(dim=128), B=2, N=300, seed=97, init="xavier", mask="padded"),
+    "d64_soft_norm":   dict(kind=L, cfg=dict(dim=64, soft_edges=True, norm_coors=True, norm_feats=True), B=2, N=96, seed=96,
+                            init="xavier", mask="random"),
+    "d72_clamp_mean":  dict(kind=L, cfg=dict(dim=72, coor_weights_clamp_value=0.5, m_pool_method="mean"), B=3, N=130, seed=95,
+                            init="xavier", mask="padded"),
+    "d64_mean_nomask": dict(kind=L, cfg=dict(dim=64, m_pool_method="mean"), B=1, N=64, seed=94, init="xavier"),
+    "d64_tiny_n":      dict(kind=L, cfg=dict(dim=64), B=2, N=5, seed=93, init="xavier"),
+    "d512_c1":         dict(kind=L, cfg=dict(dim=512), B=1, N=16, seed=92),
+    "d512_n256":       dict(kind=L, cfg=dict(dim=512), B=1, N=256, seed=91, init="xavier"),
+    "d64_no_coors":    dict(kind=L, cfg=dict(dim=64, update_coors=False), B=1, N=40, seed=90, init="xavier"),
+    "d64_no_feats":    dict(kind=L, cfg=dict(dim=64, update_feats=False), B=1, N=40, seed=89, init="xavier"),
+}
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.asarray(a, np.float64)).bfloat16().double().numpy()
+
+
+def run_fast(spec):
+    case = cases.build_case(spec)
+    case["params"] = {k: bf16_round(v) for k, v in case["params"].items()}
+    case["inputs"]["feats"] = bf16_round(case["inputs"]["feats"])
+    mod = util.make_module(case, torch.bfloat16)
+    out = util.run_module(mod, case, torch.bfloat16)
+    torch.cuda.synchronize()
+    return case, mod, out
+
+
+@pytest.mark.parametrize("name", list(FAST_SPECS))
+def test_fast_path_matches_oracle(name):
+    case, mod, out = run_fast(FAST_SPECS[name])
+    assert mod.last_path == "bf16-tcgen05"
+    assert out[0].dtype == torch.bfloat16
+    want = cases.run_oracle(case)
+    f_scale = max(1e-3, float(np.abs(want[0]).max()))
+    c_scale = float(np.abs(want[1] - case["inputs"]["coors"]).max())
+    f_err, c_err = util.max_err(out[0], want[0]), util.max_err(out[1], want[1])
+    print(f"{name}: feats err {f_err:.3e} (scale {f_scale:.3e}), coors err {c_err:.3e} (update scale {c_scale:.3e})")
+    assert np.isfinite(out[0].float().cpu().numpy()).all() and np.isfinite(out[1].float().cpu().numpy()).all()
+    assert f_err <= 3e-2 * f_scale
+    assert c_err <= 3e-2 * c_scale + 1e-3
+
+
+def test_fast_path_falls_back_to_fp32_simt_when_unsupported():
+    case = cases.build_case(cases.SPECS["knn_edges_mask"])
+    mod = util.make_module(case, torch.bfloat16)
+    out = util.run_module(mod, case, torch.bfloat16)
+    assert mod.last_path == "fp32-simt" and out[0].dtype == torch.bfloat16
+
+
+def test_fast_equivariance():
+    """tests/test_equivariance.py:8-34 on the bf16 path; coordinates and distances stay fp32, so the
+    rotation only perturbs d_ij by fp32 rounding -- the error is far below bf16 epsilon."""
+    spec = dict(kind=L, cfg=dict(dim=64), B=1, N=128, seed=5)
+    case = cases.build_case(spec)
+    mod = util.make_module(case, torch.bfloat16)
+    f = util.to_torch(case["inputs"]["feats"], torch.bfloat16, "cuda")
+    x = torch.from_numpy(case["inputs"]["coors"]).double()
+    g = torch.Generator().manual_seed(1)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    t = torch.randn(1, 1, 3, generator=g, dtype=torch.float64)
+    f1, c1 = mod(f, (x @ q + t).float().cuda())
+    f2, c2 = mod(f, x.float().cuda())
+    ef = float((f1.float() - f2.float()).abs().max())
+    ec = float((c1.double().cpu() - (c2.double().cpu() @ q + t)).abs().max())
+    print(f"bf16 path equivariance: feats {ef:.3e} coors {ec:.3e}")
+    assert ec < 1e-4
+    assert ef <= 2 ** -7 * float(f2.float().abs().max())          # at most one bf16 ulp of the output
+
+
+def test_tc_gemm_standalone():
+    import ctypes as C
+    from egnn_pytorch_b200 import _native as nat
+    lib = nat.load()
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 128, 64), (200, 136, 72), (4096, 2112, 512), (77, 1024, 528)]:
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = torch.randn(N, K, device="cuda").bfloat16()
+        bias = torch.randn(N, device="cuda")
+        o = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        rc = lib.egnn_gemm_bf16(M, N, K, A.data_ptr(), W.data_ptr(), bias.data_ptr(), 0.5, 0, o.data_ptr(), 1, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        ref = 0.5 * (A.double() @ W.double().t() + bias.double())
+        assert float((o.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-4

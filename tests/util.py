@@ -23,9 +23,10 @@ def make_module(case, dtype, device="cuda", **extra):
     from egnn_pytorch_b200 import EGNN, EGNN_Network
     spec = case["spec"]
     mod = EGNN_Network(**spec["cfg"], **extra) if case["kind"] == "network" else EGNN(**spec["cfg"], **extra)
+    mod = mod.to(dtype)                            # before loading: load_state_dict casts to the parameter dtype
     sd = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in case["params"].items()}
     mod.load_state_dict(sd, strict=True)          # reference state-dict keys must load unchanged
-    return mod.to(dtype).to(device).eval()
+    return mod.to(device).eval()
 
 
 def run_module(mod, case, dtype, device="cuda", **kw):
