@@ -34,8 +34,8 @@ class LayerDesc(C.Structure):
         ("abi_version", C.c_int32), ("dtype", C.c_int32), ("B", C.c_int32), ("N", C.c_int32),
         ("C", C.c_int32), ("dim", C.c_int32), ("edge_dim", C.c_int32), ("label_dim", C.c_int32),
         ("num_labels", C.c_int32), ("m_dim", C.c_int32), ("fourier", C.c_int32), ("k", C.c_int32),
-        ("flags", C.c_uint32), ("valid_radius", C.c_float), ("clamp", C.c_float),
-        ("row_begin", C.c_int32), ("row_end", C.c_int32),
+        ("flags", C.c_uint32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("reserved", C.c_int32),
+        ("valid_radius", C.c_double), ("clamp", C.c_double),
     ]
 
 
@@ -81,7 +81,7 @@ SYMBOLS = {
                                      C.c_size_t, C.c_void_p]),
     "egnn_layer_forward_host": (C.c_int, [_P(LayerDesc), _P(LayerWeights), C.c_void_p, _P(LayerIO), C.c_void_p]),
     "egnn_knn_select": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                  C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "egnn_adj_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),
     "egnn_adj_expand": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

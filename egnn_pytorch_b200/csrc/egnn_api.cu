@@ -8,7 +8,7 @@
 namespace egnn {
 
 int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
-                        const uint8_t* adj, int adj_batched, float valid_radius, int32_t* out_idx,
+                        const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
                         uint8_t* out_ok, cudaStream_t st);
 
 // ------------------------------------------------------------------ validation
@@ -27,6 +27,7 @@ static int validate_desc(const EgnnLayerDesc* d) {
   if (d->k > d->N) return EGNN_ERR_SHAPE;                 // torch.topk raises too (:258)
   if (d->label_dim > 0 && (d->num_labels <= 0 || d->num_labels > 255)) return EGNN_ERR_SHAPE;
   if (!(d->flags & (EGNN_FLAG_UPDATE_FEATS | EGNN_FLAG_UPDATE_COORS))) return EGNN_ERR_SHAPE;   // :171
+  if (d->reserved != 0) return EGNN_ERR_SHAPE;
   if (d->row_begin < 0 || d->row_end < 0 || d->row_end > d->N || d->row_begin > d->row_end) return EGNN_ERR_SHAPE;
   return EGNN_OK;
 }
@@ -97,7 +98,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   if (s.k > 0) {
     StageTimer tm(st, STAGE_SELECT);
     count_launch();
-    const float vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0f : d.valid_radius;     // :250
+    const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;     // :250
     EGNN_TRY(knn_select_dispatch(d.dtype, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
                                  (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
   }

@@ -256,7 +256,7 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     StageTimer tm(st, STAGE_PAIR);
     TcPairArgs a{};
     a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim;
-    a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = d.clamp; a.variant = tc_variant();
+    a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp; a.variant = tc_variant();
     a.Atab = Atab; a.Btab = Btab;
     a.wdh = reinterpret_cast<const float*>(pk + L.wdh);
     a.w2p = reinterpret_cast<const __nv_bfloat16*>(pk + L.w2p);

@@ -183,7 +183,7 @@ knn_block_sort_kernel(const SelArgs<T> a, int Npad) {
 
 template <typename T>
 static int launch_select(int B, int N, int C, int k, const void* coors, const uint8_t* mask, const uint8_t* adj,
-                         int adj_batched, float valid_radius, int32_t* out_idx, uint8_t* out_ok, cudaStream_t st) {
+                         int adj_batched, double valid_radius, int32_t* out_idx, uint8_t* out_ok, cudaStream_t st) {
   SelArgs<T> a;
   a.B = B; a.N = N; a.C = C; a.k = k;
   a.coors = static_cast<const T*>(coors);
@@ -206,7 +206,7 @@ static int launch_select(int B, int N, int C, int k, const void* coors, const ui
 }
 
 int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
-                        const uint8_t* adj, int adj_batched, float valid_radius, int32_t* out_idx,
+                        const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
                         uint8_t* out_ok, cudaStream_t st) {
   if (!coors || !out_idx) return EGNN_ERR_NULL;
   if (B <= 0 || N <= 0 || C <= 0 || C > 8 || k <= 0 || k > N) return EGNN_ERR_SHAPE;
@@ -219,7 +219,7 @@ int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* c
 
 extern "C" int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, int32_t k, const void* coors,
                                const uint8_t* mask, const uint8_t* adj, int32_t adj_batched,
-                               float valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream) {
+                               double valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream) {
   return egnn::knn_select_dispatch(dtype, B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx,
                                    out_ok, static_cast<cudaStream_t>(stream));
 }

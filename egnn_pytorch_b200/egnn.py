@@ -228,9 +228,8 @@ class EGNN(nn.Module):
             abi_version=nat.ABI_VERSION, dtype=_KERNEL_DTYPE[kdt], B=b, N=n, C=c, dim=self.dim,
             edge_dim=cont_edge_dim, label_dim=label_dim, num_labels=0 if label_emb is None else label_emb.shape[0],
             m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
-            valid_radius=float(min(self.valid_radius, 3.0e38)),
-            clamp=float(self.coor_weights_clamp_value or 0.0),
-            row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1])
+            valid_radius=float(self.valid_radius), clamp=float(self.coor_weights_clamp_value or 0.0),
+            row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0)
         w = nat.LayerWeights(**{f: (T[f].data_ptr() if f in T else None) for f in nat.WEIGHT_FIELDS})
 
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -75,10 +75,11 @@ typedef struct EgnnLayerDesc {
   int32_t  k;             /* 0 = dense all-pairs; >0 = neighbours per node, i.e. the reference's
                              use_nearest branch (:237-268) with num_nearest = k           */
   uint32_t flags;         /* EGNN_FLAG_*                                                  */
-  float    valid_radius;  /* used only when k>0 AND io.mask != NULL (:260, :296); +inf ok */
-  float    clamp;         /* coor_weights_clamp_value when EGNN_FLAG_CLAMP                */
   int32_t  row_begin;     /* evaluate i-rows [row_begin, row_end) only (row-sharded multi-GPU); */
   int32_t  row_end;       /*   0,0 = all rows.  Outputs keep their full [B,N,*] layout.   */
+  int32_t  reserved;      /* must be 0                                                    */
+  double   valid_radius;  /* used only when k>0 AND io.mask != NULL (:260, :296); +inf ok */
+  double   clamp;         /* coor_weights_clamp_value when EGNN_FLAG_CLAMP                */
 } EgnnLayerDesc;
 
 /*
@@ -158,7 +159,7 @@ int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLayerWeights* w
  * out_idx int32 [B,N,k]; out_ok uint8 [B,N,k] = (rank <= valid_radius), may be NULL. */
 int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, int32_t k,
                     const void* coors, const uint8_t* mask, const uint8_t* adj, int32_t adj_batched,
-                    float valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream);
+                    double valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream);
 
 /* N-th degree adjacency of EGNN_Network (egnn_pytorch.py:414-428) without the dense A@A:
  * adj_in [N,N] or [B,N,N] 0/1; writes the expanded adjacency adj_out [B,N,N] 0/1, the degree
