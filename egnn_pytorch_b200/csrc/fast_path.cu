@@ -3,7 +3,6 @@
 //                             -> LayerNorm/concat -> node MLP (tcgen05 GEMM x2).
 // Option sets the tensor-core kernels do not cover return EGNN_ERR_UNSUPPORTED; the binding then runs
 // the fp32 SIMT kernels (never a CPU path).
-#include <cstdlib>
 #include "fast_path.h"
 #include "profile.h"
 #include "tc_gemm.cuh"
@@ -168,13 +167,7 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   return w;
 }
 
-uint32_t tc_variant() {
-  const char* v = getenv("EGNN_TC_VARIANT");      // bring-up only: bit0 swaps LBO/SBO, bit1 swaps the bf16 pair order
-  return v ? (uint32_t)atoi(v) : 0u;
-}
-
-int launch_tc_gemm(TcGemmArgs g, cudaStream_t st) {
-  g.variant = tc_variant();
+int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
@@ -256,7 +249,7 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     StageTimer tm(st, STAGE_PAIR);
     TcPairArgs a{};
     a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim;
-    a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp; a.variant = tc_variant();
+    a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp;
     a.Atab = Atab; a.Btab = Btab;
     a.wdh = reinterpret_cast<const float*>(pk + L.wdh);
     a.w2p = reinterpret_cast<const __nv_bfloat16*>(pk + L.w2p);

@@ -22,7 +22,6 @@ struct TcGemmArgs {
   void* out; int ldo; int out_f32;
   int M, Nv, Nout, K;
   float scale; int act;               // act: 0 none, 1 SiLU
-  uint32_t variant;                   // bring-up: bit0 swaps LBO/SBO
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64;
@@ -81,7 +80,7 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_kernel(const TcGemmArgs g) {
       const uint32_t sA = s_base + (kt & 1) * 2 * GEMM_TILE_BYTES, sW = sA + GEMM_TILE_BYTES;
 #pragma unroll
       for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-        const uint32_t lbo = (g.variant & 1u) ? 128u : 2048u, sbo = (g.variant & 1u) ? 2048u : 128u;
+        constexpr uint32_t lbo = 2048u, sbo = 128u;   // K-adjacent / M-adjacent core matrices of the tile
         const uint64_t da = tc::smem_desc_kmajor_noswizzle(sA + kk * 4096, lbo, sbo);
         const uint64_t dw = tc::smem_desc_kmajor_noswizzle(sW + kk * 4096, lbo, sbo);
         tc::mma_ss(tmem, da, dw, IDESC, (kt > 0 || kk > 0) ? 1u : 0u);

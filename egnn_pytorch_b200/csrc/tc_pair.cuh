@@ -36,7 +36,7 @@ constexpr int TP_EPI_FLOATS = 64 * 16 + 64 + 64 + 16 + 16 + 4;   // W3 | b3 | w4
 
 struct TcPairArgs {
   int B, N, Hp, ldn, dim;          // ldn: row stride of node_in (bf16 elements)
-  uint32_t flags; int has_mask; float clamp; uint32_t variant;
+  uint32_t flags; int has_mask; float clamp;
   const float* Atab;               // [M][Hp]  0.5 (h W1_i^T + b1)
   const __nv_bfloat16* Btab;       // [M][Hp]  0.5 h W1_j^T
   const float* wdh;                // [Hp]     0.5 W1[:, 2dim]
@@ -173,13 +173,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
               const float y3 = fmaf(wv.w, di, av.w) + tc::bf16_hi(b23);
               const float h0 = tc::silu_half_arg(y0), h1 = tc::silu_half_arg(y1);
               const float h2 = tc::silu_half_arg(y2), h3 = tc::silu_half_arg(y3);
-              if (a.variant & 2u) {
-                hp[q * 4 + h * 2] = tc::pack_bf16x2(h1, h0);
-                hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h3, h2);
-              } else {
-                hp[q * 4 + h * 2] = tc::pack_bf16x2(h0, h1);
-                hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h2, h3);
-              }
+              hp[q * 4 + h * 2] = tc::pack_bf16x2(h0, h1);          // even k in the low half of the TMEM column
+              hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h2, h3);
             }
           }
           tc::tmem_st32(tm_wg + 128 + slot * 32, hp);
@@ -257,7 +252,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
       constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
       const uint32_t tm_g = tmem + g * 256;
       const uint32_t w2a = tc::smem_u32(w2s);
-      const uint32_t lbo = (a.variant & 1u) ? 128u : 256u, sbo = (a.variant & 1u) ? 256u : 128u;
+      constexpr uint32_t lbo = 256u, sbo = 128u;      // K-adjacent / N-adjacent core matrices of a W2 slab
       tc::mbar_wait(ldbar, 0);
       uint32_t n = 0;
       for (int jb = 0; jb < njb; ++jb) {

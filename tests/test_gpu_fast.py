@@ -40,6 +40,7 @@ def run_fast(spec):
     case = cases.build_case(spec)
     case["params"] = {k: bf16_round(v) for k, v in case["params"].items()}
     case["inputs"]["feats"] = bf16_round(case["inputs"]["feats"])
+    case["inputs"]["coors"] = bf16_round(case["inputs"]["coors"])      # a bf16 module is fed bf16 coordinates
     mod = util.make_module(case, torch.bfloat16)
     out = util.run_module(mod, case, torch.bfloat16)
     torch.cuda.synchronize()
