@@ -140,6 +140,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 
+// 16 lanes x 256 bit fragment store, 4 repeats along the columns (32 columns): thread t of the warp holds, for
+// every 8-column group n (regs 4n..4n+3), row t/4 (regs 4n, 4n+1) and row t/4 + 8 (regs 4n+2, 4n+3), columns
+// 2*(t%4) and 2*(t%4)+1 of the group -- the mma-accumulator-style layout.  The lane field of taddr selects the
+// 16-lane half (+0 / +16 inside the warp's quadrant).
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
 // ------------------------------------------------------------------ copies into shared memory
 // Ampere-style 16-byte async copy with zero-fill when src_bytes == 0 (generic proxy write).
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {

@@ -29,12 +29,11 @@ constexpr int GEMM_TILE_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB per o
 constexpr int GEMM_SMEM_BYTES = 2 * 2 * GEMM_TILE_BYTES + 1024;   // 2 stages x (A, W) + alignment slack
 
 __global__ void __launch_bounds__(128, 1) tc_gemm_kernel(const TcGemmArgs g) {
-  extern __shared__ __align__(1024) unsigned char gemm_smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t mma_done[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = tc::smem_u32(smem);
 
   if (tid == 0) { tc::mbar_init(&mma_done[0], 1); tc::mbar_init(&mma_done[1], 1); tc::mbar_fence_init(); }

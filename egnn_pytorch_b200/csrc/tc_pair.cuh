@@ -58,12 +58,13 @@ inline size_t tc_pair_smem_bytes(int Hp) {
   n += (size_t)TP_TI * 4 * 4 + 64;            // x_i, mask_i
   n += (size_t)TP_TI * TP_JB * 4;             // d_ij of the current j-block (per thread, per row)
   n += 32 * 8;                                // mbarriers
-  return n + 1024;                            // alignment slack
+  return n + 128;
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs a) {
-  extern __shared__ __align__(1024) unsigned char tp_smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tp_smem_raw) + 1023) & ~uintptr_t(1023));
+  // carve the dynamic shared memory directly (no integer round trip) so every access stays in the
+  // shared state space (LDS/STS, not generic LD/ST); nothing here needs more than 128-byte alignment
+  extern __shared__ __align__(128) unsigned char sm[];
   const int Hp = a.Hp, N = a.N;
   unsigned char* w2s = sm;                                                    // Hp*32 bytes
   float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [TI][Hp]
@@ -124,68 +125,96 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
 
   if (warp < TP_WG * 4) {
     // =========================================================== compute warpgroups
+    // Two thread<->data mappings are used:
+    //  * "pair" mapping (geometry, epilogue, tcgen05.ld 32x32b): thread t128 owns pair row t128 of the tile;
+    //  * "fragment" mapping (hidden production, tcgen05.st 16x256b): lane (lr = lane/4, lq = lane%4) owns
+    //    rows lr + 8*rho (rho = 0..3) of its warp's 32-row quadrant and, in every 16-channel K-slab, the
+    //    4 channels 4*lq .. 4*lq+3.  Lanes that share lq read the same A'/wd' words (4 distinct addresses
+    //    per warp instead of a 32-way broadcast), which is what keeps the shared-memory pipe off the
+    //    critical path; B' is read straight from L2 in 8-byte pieces that are contiguous across lq.
     const int g = warp >> 2, wq = warp & 3, t128 = tid & 127;
+    const int lr = lane >> 2, lq = lane & 3;
     const uint32_t tm_wg = tmem + g * 256 + ((uint32_t)(wq * 32) << 16);    // this warp's lane quadrant
     float* mypart = part + (size_t)warp * TP_TI * 20;
+    float* dwg = dsm + g * 128;                       // d_ij of this warpgroup's tile: dwg[i * TP_JB + pair]
     tc::mbar_wait(ldbar, 0);
     uint32_t n = 0;
     for (int jb = 0; jb < njb; ++jb) {
+      // ---- pair mapping: geometry of (i, j) for the 8 rows i
       const int j = jb * TP_JB + g * 128 + t128;
       const bool jv = j < N;
       const size_t nodej = (size_t)b * N + (jv ? j : N - 1);
       const float xj0 = a.coors[nodej * 3 + 0], xj1 = a.coors[nodej * 3 + 1], xj2 = a.coors[nodej * 3 + 2];
       const bool mask_j = jv && (a.has_mask ? a.mask[nodej] != 0 : true);
-      float* dmine = dsm + (g * 128 + t128);          // d_ij for i = 0..7 at stride 256 (private to this thread)
+      __syncwarp();                                   // previous block's readers of dwg are done
 #pragma unroll
       for (int i = 0; i < TP_TI; ++i) {
         const float r0 = xis[i * 4 + 0] - xj0, r1 = xis[i * 4 + 1] - xj1, r2 = xis[i * 4 + 2] - xj2;
-        dmine[i * TP_JB] = r0 * r0 + r1 * r1 + r2 * r2;
+        dwg[i * TP_JB + t128] = r0 * r0 + r1 * r1 + r2 * r2;
       }
-      const uint4* Bp = reinterpret_cast<const uint4*>(a.Btab + nodej * Hp);
-      uint4 Bcur[8], Bnxt[8];
+      __syncwarp();
+      // ---- fragment mapping: B' rows of this lane's 4 pairs
+      const uint2* Bp[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) Bcur[q] = __ldg(Bp + q);
+      for (int rho = 0; rho < 4; ++rho) {
+        const int jr = jb * TP_JB + g * 128 + wq * 32 + lr + 8 * rho;
+        Bp[rho] = reinterpret_cast<const uint2*>(a.Btab + ((size_t)b * N + min(jr, N - 1)) * Hp + 4 * lq);
+      }
+      uint2 Bc[4][4];                                 // [rho][slab] B' of the current chunk (bf16 x4 each)
+#pragma unroll
+      for (int rho = 0; rho < 4; ++rho)
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = __ldg(Bp[rho] + sl * 4);
 
       for (int c = 0; c < nchunks; ++c) {
-        if (c + 1 < nchunks) {
+        float4 wdr[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) Bnxt[q] = __ldg(Bp + (c + 1) * 8 + q);
-        }
-        const float4* W4 = reinterpret_cast<const float4*>(wds + c * TP_KC);
-#pragma unroll 1
-        for (int i = 0; i < TP_TI; ++i, ++n) {
+        for (int sl = 0; sl < 4; ++sl) wdr[sl] = *reinterpret_cast<const float4*>(wds + c * TP_KC + sl * 16 + lq * 4);
+        // One round = the 64 hidden channels of chunk c for row i and this warp's 32 pairs.  In the last round
+        // of a chunk (`reload`), every B' register is re-filled for chunk c+1 right after its last use, so the
+        // L2 latency is covered by the rest of that round without a second register buffer.
+        auto round = [&](int i, bool reload) {
           const uint32_t slot = n & (TP_SLOTS - 1);
+          float dr[4];
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) dr[rho] = dwg[i * TP_JB + wq * 32 + lr + 8 * rho];
           tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n >> 2) & 1) ^ 1);
           tc::tc_fence_after();
-          const float4* A4 = reinterpret_cast<const float4*>(As + (size_t)i * Hp + c * TP_KC);
-          const float di = dmine[i * TP_JB];
-          uint32_t hp[32];
+          const float* Ai = As + (size_t)i * Hp + c * TP_KC + lq * 4;
+          const uint32_t ta = tm_wg + 128 + slot * 32;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint32_t bw[4] = {Bcur[q].x, Bcur[q].y, Bcur[q].z, Bcur[q].w};
+          for (int half = 0; half < 2; ++half) {       // rows (lr, lr+8), then (lr+16, lr+24)
+            uint32_t hp[16];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float4 av = A4[q * 2 + h], wv = W4[q * 2 + h];
-              const uint32_t b01 = bw[h * 2], b23 = bw[h * 2 + 1];
-              const float y0 = fmaf(wv.x, di, av.x) + tc::bf16_lo(b01);
-              const float y1 = fmaf(wv.y, di, av.y) + tc::bf16_hi(b01);
-              const float y2 = fmaf(wv.z, di, av.z) + tc::bf16_lo(b23);
-              const float y3 = fmaf(wv.w, di, av.w) + tc::bf16_hi(b23);
-              const float h0 = tc::silu_half_arg(y0), h1 = tc::silu_half_arg(y1);
-              const float h2 = tc::silu_half_arg(y2), h3 = tc::silu_half_arg(y3);
-              hp[q * 4 + h * 2] = tc::pack_bf16x2(h0, h1);          // even k in the low half of the TMEM column
-              hp[q * 4 + h * 2 + 1] = tc::pack_bf16x2(h2, h3);
+            for (int sl = 0; sl < 4; ++sl) {
+              const float4 av = *reinterpret_cast<const float4*>(Ai + sl * 16);
+              const float4 wv = wdr[sl];
+#pragma unroll
+              for (int r2 = 0; r2 < 2; ++r2) {
+                const int rho = half * 2 + r2;
+                const uint2 bb = Bc[rho][sl];
+                const float d = dr[rho];
+                const float y0 = fmaf(wv.x, d, av.x) + tc::bf16_lo(bb.x);
+                const float y1 = fmaf(wv.y, d, av.y) + tc::bf16_hi(bb.x);
+                const float y2 = fmaf(wv.z, d, av.z) + tc::bf16_lo(bb.y);
+                const float y3 = fmaf(wv.w, d, av.w) + tc::bf16_hi(bb.y);
+                // 16x256b fragment: regs {0,1} of a slab -> row lr (+16), regs {2,3} -> row lr+8 (+24); even k low
+                hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
+                hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
+                if (reload) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
+              }
             }
+            tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
           }
-          tc::tmem_st32(tm_wg + 128 + slot * 32, hp);
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::mbar_arrive(&full[g * TP_SLOTS + slot]);
-        }
-        if (c + 1 < nchunks) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) Bcur[q] = Bnxt[q];
-        }
+          ++n;
+        };
+#pragma unroll 1
+        for (int i = 0; i < TP_TI - 1; ++i) round(i, false);
+        if (c + 1 < nchunks) round(TP_TI - 1, true);
+        else round(TP_TI - 1, false);
       }
 
       // ---- epilogue of this j-block: accumulators back to the owning thread
@@ -228,7 +257,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           }
           if (!pm) w = 0.f;                                                                               // :309
           if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);                          // :313
-          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dmine[i * TP_JB]), 1e-8f);                  // :74-77
+          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dwg[i * TP_JB + t128]), 1e-8f);                  // :74-77
         }
         v[16] = w * (xis[i * 4 + 0] - xj0); v[17] = w * (xis[i * 4 + 1] - xj1); v[18] = w * (xis[i * 4 + 2] - xj2);
         v[19] = pm ? 1.f : 0.f;

@@ -1,0 +1,26 @@
+"""Summarise an .ncu-rep (first kernel) into the handful of numbers DESIGN.md / profiles/ cite."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2]
+d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "sm__warps_active.avg.per_cycle_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed"]
+for k in keys:
+    if k in d:
+        print(f"{k:80s} {d[k][0]} {d[k][1]}")
+print("-- warp stall reasons (warps per issue-active cycle)")
+for h in hdr:
+    if h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio"):
+        v = float(d[h][0])
+        if v > 0.05:
+            print(f"   {h.split('stalled_')[1].split('_per_issue')[0]:28s} {v:.3f}")
