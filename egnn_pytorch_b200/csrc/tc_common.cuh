@@ -43,6 +43,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, with a nanosleep back-off: for the single-lane MMA issuer, whose polling would otherwise
+// steal issue slots from the compute warps of its SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > (1u << 26)) { asm volatile("trap;"); }
+  }
+}
+
 // ------------------------------------------------------------------ proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -181,6 +191,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// c + (low / high bf16 half of u), one mixed-precision FHADD.BF16 each: the packed operand is consumed
+// through the .H0/.H1 register selectors, so no unpack instruction (and no fp32 copy of B') is needed.
+__device__ __forceinline__ float add_bf16_lo(uint32_t u, float c) {
+  float y;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(y) : "r"(u), "f"(c));
+  return y;
+}
+__device__ __forceinline__ float add_bf16_hi(uint32_t u, float c) {
+  float y;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(y) : "r"(u), "f"(c));
+  return y;
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }

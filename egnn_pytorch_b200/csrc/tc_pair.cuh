@@ -4,20 +4,30 @@
 // [h_i | h_j | d]), :289-290 (gate), :292-333 (masks, coors MLP, clamp, both sums over j).
 //
 // Per pair (i, j) the split form needs  hidden[c] = SiLU(A_i[c] + B_j[c] + wd[c] d_ij), c < H, and
-// m_pre = hidden . W2^T  (H -> 16).  One CTA owns TI = 8 query rows i and walks all j in blocks of 256:
-//   * 2 compute warpgroups (128 threads each); a thread owns one neighbour j of the block and produces,
-//     for each of the 8 rows i and each 64-wide hidden chunk, the 64 bf16 hidden values of pair (i, j)
-//     in registers (fp32 math, one MUFU.TANH per value) and stores them with tcgen05.st into a TMEM
-//     slot laid out as the A operand (lane = pair, 32 columns = 64 bf16) -- the O(N^2 H) hidden tensor
-//     lives only in TMEM, 8 KB at a time;
-//   * 1 MMA warp per warpgroup: tcgen05.mma.kind::f16 (M=128 pairs, N=16, K=16) x4 per chunk with A from
-//     TMEM and B = the W2 slab from shared memory, accumulating m_pre[i] (128 x 16 fp32) in TMEM across
-//     all chunks; slot hand-over through full/empty mbarriers (tcgen05.commit);
-//   * after the last chunk the same threads read their pair's 16 accumulators back (tcgen05.ld), apply
-//     SiLU / gate / coors MLP / mask / clamp in fp32 and reduce over j with warp shuffles; per-row sums
-//     sum_j m_ij and sum_j w_ij (x_i - x_j) are kept in shared memory and written once per row.
-// W2 (packed in UMMA core-matrix order), the 8 A_i rows and wd are staged once per CTA with TMA bulk
-// copies (cp.async.bulk -> UBLKCP) onto an mbarrier.
+// m_pre = hidden . W2^T  (H -> 16).  One CTA owns TI = 4 query rows i and walks all j in blocks of 512:
+//   * 4 compute warpgroups (128 threads each) -- 4 warps per SM sub-partition, which is what it takes
+//     to keep the MUFU pipe fed (round-1 profile: 2 warps/SMSP left it 54 % idle on fixed-latency
+//     stalls).  A warpgroup owns 128 neighbours j.  For each hidden chunk of 64 channels and each row i
+//     it produces the 64 bf16 hidden values of its 128 pairs in registers (fp32 math, one MUFU.TANH per
+//     value) and stores them with tcgen05.st into a TMEM slot laid out as the MMA A operand (lane = pair,
+//     32 columns = 64 bf16): the O(N^2 H) hidden tensor only ever exists 8 KB at a time, in TMEM;
+//   * the MMAs are issued by the compute warps themselves (a 17th warp would cut the register budget from
+//     128 to 96): after storing round n, warp n%4 of the warpgroup waits for the other three to arrive on
+//     the slot's `full` mbarrier and one lane issues tcgen05.mma.kind::f16 (M=128 pairs, N=16, K=16) x4
+//     with A from TMEM and B = the W2 slab from shared memory, accumulating m_pre[i] (128 x 16 fp32) in
+//     TMEM across all chunks; tcgen05.commit releases the slot through its `empty` mbarrier;
+//   * after the last chunk each thread reads its own pair's 16 accumulators back (tcgen05.ld), applies
+//     SiLU / gate / coors MLP / mask / clamp in fp32 and the warp reduces over j with shuffles; per-row
+//     sums  sum_j m_ij  and  sum_j w_ij (x_i - x_j)  live in shared memory and are written once per row.
+// W2 (packed in UMMA core-matrix order), the A_i rows and wd are staged once per CTA with TMA bulk copies
+// (cp.async.bulk -> UBLKCP) onto an mbarrier.
+//
+// Thread <-> data mappings inside a compute warp:
+//   "pair" mapping     (geometry, epilogue, tcgen05.ld 32x32b): lane l owns pair row 32*wq + l of the tile;
+//   "fragment" mapping (hidden production, tcgen05.st 16x256b): lane (lr = l/4, lq = l%4) owns rows
+//     lr + 8*rho (rho = 0..3) of the warp's 32-row quadrant and, in every 16-channel K-slab, channels
+//     4*lq .. 4*lq+3.  Lanes sharing lq read the same A'/wd words (4 distinct addresses per warp instead
+//     of a 32-way broadcast, which cost one shared-memory wavefront per 4 bytes in the first version).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -26,13 +36,16 @@
 
 namespace egnn {
 
-constexpr int TP_TI = 8;          // query rows per CTA
+constexpr int TP_TI = 4;          // query rows per CTA
 constexpr int TP_KC = 64;         // hidden channels per chunk (= 32 TMEM columns, 4 MMAs)
-constexpr int TP_SLOTS = 4;       // A-operand slots per warpgroup
-constexpr int TP_WG = 2;          // compute warpgroups
-constexpr int TP_THREADS = TP_WG * 128 + TP_WG * 32;
-constexpr int TP_JB = TP_WG * 128;   // neighbours per block
+constexpr int TP_SLOTS = 2;       // A-operand slots per warpgroup
+constexpr int TP_WG = 4;          // compute warpgroups
+constexpr int TP_CWARPS = TP_WG * 4;
+constexpr int TP_THREADS = TP_WG * 128;      // 16 warps = 4 per SM sub-partition, 128 registers each
+constexpr int TP_JB = TP_WG * 128;    // neighbours per block
+constexpr int TP_WGCOLS = 128;        // TMEM columns per warpgroup: TI*16 accumulators + SLOTS*32 operand
 constexpr int TP_EPI_FLOATS = 64 * 16 + 64 + 64 + 16 + 16 + 4;   // W3 | b3 | w4 | b2 | gate_w | gate_b, b4, scale, 0
+static_assert(TP_TI * 16 + TP_SLOTS * 32 == TP_WGCOLS && TP_WG * TP_WGCOLS == 512, "TMEM budget");
 
 struct TcPairArgs {
   int B, N, Hp, ldn, dim;          // ldn: row stride of node_in (bf16 elements)
@@ -54,9 +67,9 @@ inline size_t tc_pair_smem_bytes(int Hp) {
   n += (size_t)TP_TI * Hp * 4;                // A rows (fp32)
   n += (size_t)Hp * 4;                        // wd
   n += (size_t)TP_EPI_FLOATS * 4;             // epilogue constants
-  n += (size_t)TP_WG * 4 * TP_TI * 20 * 4;    // per-warp partial sums
-  n += (size_t)TP_TI * 4 * 4 + 64;            // x_i, mask_i
-  n += (size_t)TP_TI * TP_JB * 4;             // d_ij of the current j-block (per thread, per row)
+  n += (size_t)TP_CWARPS * TP_TI * 20 * 4;    // per-warp partial sums
+  n += (size_t)TP_TI * 4 * 4 + 64;            // x_i, mask_i, tmem pointer
+  n += (size_t)TP_TI * TP_JB * 4;             // d_ij of the current j-block
   n += 32 * 8;                                // mbarriers
   return n + 128;
 }
@@ -70,15 +83,15 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
   float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [TI][Hp]
   float* wds = As + (size_t)TP_TI * Hp;                                       // [Hp]
   float* epi = wds + Hp;                                                      // constants
-  float* part = epi + TP_EPI_FLOATS;                                          // [8 warps][TI][20]
-  float* xis = part + TP_WG * 4 * TP_TI * 20;                                 // [TI][4]
+  float* part = epi + TP_EPI_FLOATS;                                          // [16 warps][TI][20]
+  float* xis = part + TP_CWARPS * TP_TI * 20;                                 // [TI][4]
   uint32_t* mki = reinterpret_cast<uint32_t*>(xis + TP_TI * 4);               // [TI] (+ tmem ptr at [15])
-  float* dsm = reinterpret_cast<float*>(mki + 16);                            // [TI][256]
+  float* dsm = reinterpret_cast<float*>(mki + 16);                            // [TI][TP_JB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm + TP_TI * TP_JB);
-  uint64_t* full = bars;                       // [WG][SLOTS]
-  uint64_t* empty = bars + TP_WG * TP_SLOTS;   // [WG][SLOTS]
-  uint64_t* accdone = empty + TP_WG * TP_SLOTS;  // [WG]
-  uint64_t* ldbar = accdone + TP_WG;           // staging barrier
+  uint64_t* full = bars;                          // [WG][SLOTS]
+  uint64_t* empty = bars + TP_WG * TP_SLOTS;      // [WG][SLOTS]
+  uint64_t* accdone = empty + TP_WG * TP_SLOTS;   // [WG]
+  uint64_t* ldbar = accdone + TP_WG;              // staging barrier
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, i0 = blockIdx.x * TP_TI;
@@ -94,9 +107,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
     tc::mbar_init(ldbar, 1);
     tc::mbar_fence_init();
   }
-  if (warp == TP_WG * 4) tc::tmem_alloc<512>(&mki[15]);
+  if (warp == 0) tc::tmem_alloc<512>(&mki[15]);
   for (int x = tid; x < TP_EPI_FLOATS; x += TP_THREADS) epi[x] = a.epi[x];
-  for (int x = tid; x < TP_WG * 4 * TP_TI * 20; x += TP_THREADS) part[x] = 0.f;
+  for (int x = tid; x < TP_CWARPS * TP_TI * 20; x += TP_THREADS) part[x] = 0.f;
   if (tid < TP_TI) {
     const bool v = tid < rows_valid;
     const size_t node = (size_t)b * N + (v ? i0 + tid : i0);
@@ -123,24 +136,20 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
     bulk(tc::smem_u32(wds), reinterpret_cast<const unsigned char*>(a.wdh), wd_bytes);
   }
 
-  if (warp < TP_WG * 4) {
+  {
     // =========================================================== compute warpgroups
-    // Two thread<->data mappings are used:
-    //  * "pair" mapping (geometry, epilogue, tcgen05.ld 32x32b): thread t128 owns pair row t128 of the tile;
-    //  * "fragment" mapping (hidden production, tcgen05.st 16x256b): lane (lr = lane/4, lq = lane%4) owns
-    //    rows lr + 8*rho (rho = 0..3) of its warp's 32-row quadrant and, in every 16-channel K-slab, the
-    //    4 channels 4*lq .. 4*lq+3.  Lanes that share lq read the same A'/wd' words (4 distinct addresses
-    //    per warp instead of a 32-way broadcast), which is what keeps the shared-memory pipe off the
-    //    critical path; B' is read straight from L2 in 8-byte pieces that are contiguous across lq.
     const int g = warp >> 2, wq = warp & 3, t128 = tid & 127;
     const int lr = lane >> 2, lq = lane & 3;
-    const uint32_t tm_wg = tmem + g * 256 + ((uint32_t)(wq * 32) << 16);    // this warp's lane quadrant
+    const uint32_t tm_wg = tmem + g * TP_WGCOLS + ((uint32_t)(wq * 32) << 16);    // this warp's lane quadrant
     float* mypart = part + (size_t)warp * TP_TI * 20;
     float* dwg = dsm + g * 128;                       // d_ij of this warpgroup's tile: dwg[i * TP_JB + pair]
+    constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
+    const uint32_t w2a = tc::smem_u32(w2s);           // W2 slab s at +512*s: K-adjacent core matrices 256 B apart, N-adjacent 128 B
     tc::mbar_wait(ldbar, 0);
-    uint32_t n = 0;
+    uint32_t n = 0;                                   // rounds this warpgroup has produced
     for (int jb = 0; jb < njb; ++jb) {
-      // ---- pair mapping: geometry of (i, j) for the 8 rows i
+      if (jb * TP_JB + g * 128 >= N) break;           // this warpgroup's tile lies beyond the graph
+      // ---- pair mapping: geometry of (i, j) for the rows i
       const int j = jb * TP_JB + g * 128 + t128;
       const bool jv = j < N;
       const size_t nodej = (size_t)b * N + (jv ? j : N - 1);
@@ -167,9 +176,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = __ldg(Bp[rho] + sl * 4);
 
       for (int c = 0; c < nchunks; ++c) {
-        float4 wdr[4];
-#pragma unroll
-        for (int sl = 0; sl < 4; ++sl) wdr[sl] = *reinterpret_cast<const float4*>(wds + c * TP_KC + sl * 16 + lq * 4);
         // One round = the 64 hidden channels of chunk c for row i and this warp's 32 pairs.  In the last round
         // of a chunk (`reload`), every B' register is re-filled for chunk c+1 right after its last use, so the
         // L2 latency is covered by the rest of that round without a second register buffer.
@@ -178,26 +184,27 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           float dr[4];
 #pragma unroll
           for (int rho = 0; rho < 4; ++rho) dr[rho] = dwg[i * TP_JB + wq * 32 + lr + 8 * rho];
-          tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n >> 2) & 1) ^ 1);
+          tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n / TP_SLOTS) & 1) ^ 1);
           tc::tc_fence_after();
           const float* Ai = As + (size_t)i * Hp + c * TP_KC + lq * 4;
-          const uint32_t ta = tm_wg + 128 + slot * 32;
+          const float* Wc = wds + c * TP_KC + lq * 4;
+          const uint32_t ta = tm_wg + TP_TI * 16 + slot * 32;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {       // rows (lr, lr+8), then (lr+16, lr+24)
             uint32_t hp[16];
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {
               const float4 av = *reinterpret_cast<const float4*>(Ai + sl * 16);
-              const float4 wv = wdr[sl];
+              const float4 wv = *reinterpret_cast<const float4*>(Wc + sl * 16);
 #pragma unroll
               for (int r2 = 0; r2 < 2; ++r2) {
                 const int rho = half * 2 + r2;
                 const uint2 bb = Bc[rho][sl];
                 const float d = dr[rho];
-                const float y0 = fmaf(wv.x, d, av.x) + tc::bf16_lo(bb.x);
-                const float y1 = fmaf(wv.y, d, av.y) + tc::bf16_hi(bb.x);
-                const float y2 = fmaf(wv.z, d, av.z) + tc::bf16_lo(bb.y);
-                const float y3 = fmaf(wv.w, d, av.w) + tc::bf16_hi(bb.y);
+                const float y0 = tc::add_bf16_lo(bb.x, fmaf(wv.x, d, av.x));
+                const float y1 = tc::add_bf16_hi(bb.x, fmaf(wv.y, d, av.y));
+                const float y2 = tc::add_bf16_lo(bb.y, fmaf(wv.z, d, av.z));
+                const float y3 = tc::add_bf16_hi(bb.y, fmaf(wv.w, d, av.w));
                 // 16x256b fragment: regs {0,1} of a slab -> row lr (+16), regs {2,3} -> row lr+8 (+24); even k low
                 hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
                 hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
@@ -209,6 +216,21 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::mbar_arrive(&full[g * TP_SLOTS + slot]);
+          if ((n & 3u) == (uint32_t)wq) {               // rotating duty: this warp issues round n's MMAs
+            tc::mbar_wait(&full[g * TP_SLOTS + slot], (n / TP_SLOTS) & 1);
+            tc::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t tm_g = tmem + g * TP_WGCOLS;
+#pragma unroll
+              for (int kk = 0; kk < TP_KC / 16; ++kk) {
+                const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(c * 4 + kk) * 512, 256u, 128u);
+                tc::mma_ts(tm_g + i * 16, tm_g + TP_TI * 16 + slot * 32 + kk * 8, bd, IDESC, (c > 0 || kk > 0) ? 1u : 0u);
+              }
+              tc::mma_commit(&empty[g * TP_SLOTS + slot]);
+              if (c + 1 == nchunks && i + 1 == TP_TI) tc::mma_commit(&accdone[g]);
+            }
+            __syncwarp();
+          }
           ++n;
         };
 #pragma unroll 1
@@ -217,7 +239,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         else round(TP_TI - 1, false);
       }
 
-      // ---- epilogue of this j-block: accumulators back to the owning thread
+      // ---- epilogue of this j-block: accumulators back to the owning thread (pair mapping)
       tc::mbar_wait(&accdone[g], jb & 1);
       tc::tc_fence_after();
       const float* W3 = epi; const float* b3 = epi + 1024; const float* w4 = b3 + 64;
@@ -257,7 +279,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           }
           if (!pm) w = 0.f;                                                                               // :309
           if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);                          // :313
-          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dwg[i * TP_JB + t128]), 1e-8f);                  // :74-77
+          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dwg[i * TP_JB + t128]), 1e-8f);    // :74-77
         }
         v[16] = w * (xis[i * 4 + 0] - xj0); v[17] = w * (xis[i * 4 + 1] - xj1); v[18] = w * (xis[i * 4 + 2] - xj2);
         v[19] = pm ? 1.f : 0.f;
@@ -274,34 +296,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
       }
       tc::tc_fence_before();
     }
-  } else {
-    // =========================================================== MMA issuers (one warp per warpgroup)
-    const int g = warp - TP_WG * 4;
-    if (lane == 0) {
-      constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
-      const uint32_t tm_g = tmem + g * 256;
-      const uint32_t w2a = tc::smem_u32(w2s);
-      constexpr uint32_t lbo = 256u, sbo = 128u;      // K-adjacent / N-adjacent core matrices of a W2 slab
-      tc::mbar_wait(ldbar, 0);
-      uint32_t n = 0;
-      for (int jb = 0; jb < njb; ++jb) {
-        for (int c = 0; c < nchunks; ++c) {
-          for (int i = 0; i < TP_TI; ++i, ++n) {
-            const uint32_t slot = n & (TP_SLOTS - 1);
-            tc::mbar_wait(&full[g * TP_SLOTS + slot], (n >> 2) & 1);
-            tc::tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < TP_KC / 16; ++kk) {
-              const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(c * 4 + kk) * 512, lbo, sbo);
-              tc::mma_ts(tm_g + i * 16, tm_g + 128 + slot * 32 + kk * 8, bd, IDESC, (c > 0 || kk > 0) ? 1u : 0u);
-            }
-            tc::mma_commit(&empty[g * TP_SLOTS + slot]);
-          }
-        }
-        tc::mma_commit(&accdone[g]);
-      }
-    }
-    __syncwarp();
   }
 
   // ---------------- per-row outputs
@@ -312,14 +306,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
     if (i < rows_valid) {
       float s = 0.f;
 #pragma unroll
-      for (int wv = 0; wv < TP_WG * 4; ++wv) s += part[(size_t)wv * TP_TI * 20 + i * 20 + o];
+      for (int wv = 0; wv < TP_CWARPS; ++wv) s += part[(size_t)wv * TP_TI * 20 + i * 20 + o];
       const size_t node = (size_t)b * N + i0 + i;
       if (o < 16) {
         if (upd_feats) {
           float inv = 1.f;
           if (a.flags & EGNN_FLAG_POOL_MEAN) {
             float cnt = 0.f;
-            for (int wv = 0; wv < TP_WG * 4; ++wv) cnt += part[(size_t)wv * TP_TI * 20 + i * 20 + 19];
+            for (int wv = 0; wv < TP_CWARPS; ++wv) cnt += part[(size_t)wv * TP_TI * 20 + i * 20 + 19];
             inv = a.has_mask ? (cnt > 0.f ? 1.f / cnt : 0.f) : 1.f / (float)N;                            // :325-330
           }
           a.m_out[node * a.ldn + o] = __float2bfloat16(s * inv);
@@ -330,7 +324,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
     }
   }
   __syncthreads();
-  if (warp == TP_WG * 4) tc::tmem_dealloc<512>(tmem);
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
 }  // namespace egnn
