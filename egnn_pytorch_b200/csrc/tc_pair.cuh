@@ -175,19 +175,44 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = __ldg(Bp[rho] + sl * 4);
 
+      int pend_c = 0, pend_i = 0;
+      uint32_t pend_n = 0;
+      bool pend_valid = false;
+      auto issue_pending = [&]() {
+        if (!pend_valid) return;
+        pend_valid = false;
+        if ((pend_n & 3u) != (uint32_t)wq) return;      // rotating duty: warp (round % 4) of the warpgroup issues
+        const uint32_t pslot = pend_n & (TP_SLOTS - 1);
+        tc::mbar_wait(&full[g * TP_SLOTS + pslot], (pend_n / TP_SLOTS) & 1);
+        tc::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tm_g = tmem + g * TP_WGCOLS;
+#pragma unroll
+          for (int kk = 0; kk < TP_KC / 16; ++kk) {
+            const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(pend_c * 4 + kk) * 512, 256u, 128u);
+            tc::mma_ts(tm_g + pend_i * 16, tm_g + TP_TI * 16 + pslot * 32 + kk * 8, bd, IDESC, (pend_c > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc::mma_commit(&empty[g * TP_SLOTS + pslot]);
+          if (pend_c + 1 == nchunks && pend_i + 1 == TP_TI) tc::mma_commit(&accdone[g]);
+        }
+        __syncwarp();
+      };
       for (int c = 0; c < nchunks; ++c) {
+        float4 wdr[4];                                // wd of this lane's 16 channels of the chunk
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) wdr[sl] = *reinterpret_cast<const float4*>(wds + c * TP_KC + sl * 16 + lq * 4);
         // One round = the 64 hidden channels of chunk c for row i and this warp's 32 pairs.  In the last round
         // of a chunk (`reload`), every B' register is re-filled for chunk c+1 right after its last use, so the
         // L2 latency is covered by the rest of that round without a second register buffer.
+        // MMA issue is deferred by half a round: the MMAs of round n-1 are issued (by warp (n-1)%4 of the
+        // warpgroup) in the middle of round n, when the other three warps have long arrived, and the slot of
+        // round n is only waited for right before its first tcgen05.st.
         auto round = [&](int i, bool reload) {
           const uint32_t slot = n & (TP_SLOTS - 1);
           float dr[4];
 #pragma unroll
           for (int rho = 0; rho < 4; ++rho) dr[rho] = dwg[i * TP_JB + wq * 32 + lr + 8 * rho];
-          tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n / TP_SLOTS) & 1) ^ 1);
-          tc::tc_fence_after();
           const float* Ai = As + (size_t)i * Hp + c * TP_KC + lq * 4;
-          const float* Wc = wds + c * TP_KC + lq * 4;
           const uint32_t ta = tm_wg + TP_TI * 16 + slot * 32;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {       // rows (lr, lr+8), then (lr+16, lr+24)
@@ -195,7 +220,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {
               const float4 av = *reinterpret_cast<const float4*>(Ai + sl * 16);
-              const float4 wv = *reinterpret_cast<const float4*>(Wc + sl * 16);
+              const float4 wv = wdr[sl];
 #pragma unroll
               for (int r2 = 0; r2 < 2; ++r2) {
                 const int rho = half * 2 + r2;
@@ -211,26 +236,17 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
                 if (reload) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
               }
             }
+            if (half == 0) {
+              issue_pending();                          // round n-1's MMAs, if this warp has the duty
+              tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n / TP_SLOTS) & 1) ^ 1);
+              tc::tc_fence_after();
+            }
             tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
           }
           tc::tmem_wait_st();
           tc::tc_fence_before();
           tc::mbar_arrive(&full[g * TP_SLOTS + slot]);
-          if ((n & 3u) == (uint32_t)wq) {               // rotating duty: this warp issues round n's MMAs
-            tc::mbar_wait(&full[g * TP_SLOTS + slot], (n / TP_SLOTS) & 1);
-            tc::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t tm_g = tmem + g * TP_WGCOLS;
-#pragma unroll
-              for (int kk = 0; kk < TP_KC / 16; ++kk) {
-                const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(c * 4 + kk) * 512, 256u, 128u);
-                tc::mma_ts(tm_g + i * 16, tm_g + TP_TI * 16 + slot * 32 + kk * 8, bd, IDESC, (c > 0 || kk > 0) ? 1u : 0u);
-              }
-              tc::mma_commit(&empty[g * TP_SLOTS + slot]);
-              if (c + 1 == nchunks && i + 1 == TP_TI) tc::mma_commit(&accdone[g]);
-            }
-            __syncwarp();
-          }
+          pend_c = c; pend_i = i; pend_n = n; pend_valid = true;
           ++n;
         };
 #pragma unroll 1
@@ -238,6 +254,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         if (c + 1 < nchunks) round(TP_TI - 1, true);
         else round(TP_TI - 1, false);
       }
+      issue_pending();                                  // last round of the block: also signals accdone
 
       // ---- epilogue of this j-block: accumulators back to the owning thread (pair mapping)
       tc::mbar_wait(&accdone[g], jb & 1);
