@@ -1,0 +1,155 @@
+"""The five BASELINE.json configurations at (or near) full size on the GPU.
+
+Full-size value parity against the oracle is affordable for c1, c3 and a row block of c2/c4/c5;
+where the whole output cannot be checked against the CPU in seconds, size-independent properties are
+used instead: E(n) equivariance, invariance to padding content, permutation
+equivariance over nodes, batch independence, determinism."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def rotation(seed=0):
+    g = torch.Generator().manual_seed(seed)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    return q, torch.randn(1, 1, 3, generator=g, dtype=torch.float64)
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------ c1: EGNN(dim=512), B=1, N=16 (README example)
+def test_c1_exact_fp32_and_bf16():
+    spec = dict(kind="layer", cfg=dict(dim=512), B=1, N=16, seed=20)
+    case = cases.build_case(spec)
+    want = cases.run_oracle(case)
+    mod = util.make_module(case, torch.float32)
+    out = util.run_module(mod, case, torch.float32)
+    util.assert_close(out[0], want[0], atol=2e-6, rtol=1e-5, what="c1 feats")      # default init: SURVEY 8(c) gate 2e-6
+    util.assert_close(out[1], want[1], atol=2e-6, rtol=1e-5, what="c1 coors")
+    modb = util.make_module(case, torch.bfloat16)
+    outb = util.run_module(modb, case, torch.bfloat16)
+    assert modb.last_path == "bf16-tcgen05"
+    assert rel_err(outb[0], torch.from_numpy(want[0])) < 2e-2
+
+
+# ------------------------------------------------------------------ c2: EGNN(dim=512) dense, B=4, N=1024
+@pytest.mark.parametrize("dtype,path,tol", [(torch.bfloat16, "bf16-tcgen05", 2e-2), (torch.float32, "fp32-simt", 1e-4)],
+                         ids=["bf16", "fp32"])
+def test_c2_full_size_row_block_vs_oracle_and_properties(dtype, path, tol):
+    B, N, d = 4, 1024, 512
+    spec = dict(kind="layer", cfg=dict(dim=d), B=B, N=N, seed=2)
+    case = cases.build_case(spec)
+    if dtype == torch.bfloat16:
+        r = lambda v: torch.from_numpy(np.asarray(v, np.float64)).bfloat16().double().numpy()
+        case["params"] = {k: r(v) for k, v in case["params"].items()}
+        case["inputs"]["feats"] = r(case["inputs"]["feats"])
+        case["inputs"]["coors"] = r(case["inputs"]["coors"])
+    mod = util.make_module(case, dtype)
+    feats = util.to_torch(case["inputs"]["feats"], dtype, "cuda")
+    coors = torch.from_numpy(case["inputs"]["coors"]).float().cuda()
+    f, x = mod(feats, coors)
+    assert mod.last_path == path
+    # value parity on a row block of graph 2 (the oracle needs the whole graph as neighbours, not all rows)
+    ins = case["inputs"]
+    wf, wx = cases.O.egnn_layer_forward(case["params"], case["cfg"], ins["feats"][2:3], ins["coors"][2:3], rows=(500, 532))
+    assert rel_err(f[2:3, 500:532], torch.from_numpy(wf)) < tol
+    upd = float(np.abs(wx - ins["coors"][2:3, 500:532]).max())
+    assert float((x[2:3, 500:532].double().cpu() - torch.from_numpy(wx)).abs().max()) < tol * max(upd, 1.0)
+    # batch independence: graph 2 alone gives the same rows
+    f1, x1 = mod(feats[2:3], coors[2:3])
+    assert torch.equal(f1, f[2:3]) and torch.equal(x1, x[2:3])
+    # determinism
+    f2, x2 = mod(feats, coors)
+    assert torch.equal(f, f2) and torch.equal(x, x2)
+    # E(n) equivariance (tests/test_equivariance.py:8-34): feats invariant, coors equivariant
+    q, t = rotation(3)
+    fr, xr = mod(feats, (coors.double().cpu() @ q + t).float().cuda())
+    assert float((fr.float() - f.float()).abs().max()) <= (2 ** -7 if dtype == torch.bfloat16 else 2e-5) * float(f.float().abs().max())
+    want_x = x.double().cpu() @ q + t
+    assert float((xr.double().cpu() - want_x).abs().max()) <= 2e-6 * float(want_x.abs().max()) + 1e-5
+    # node-permutation equivariance
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(5)).cuda()
+    fp, xp = mod(feats[:, perm], coors[:, perm])
+    assert rel_err(fp, f[:, perm]) < (2e-2 if dtype == torch.bfloat16 else 1e-4)
+
+
+# ------------------------------------------------------------------ c3: EGNN_Network depth 3, dim 32, N=1024, k=8, mask
+def test_c3_full_size_vs_oracle():
+    spec = dict(kind="network", cfg=dict(depth=3, dim=32, num_tokens=21, num_positions=1024, num_nearest_neighbors=8,
+                                         coor_weights_clamp_value=2.0), B=1, N=1024, seed=3, mask="padded")
+    case = cases.build_case(spec)
+    want = cases.run_oracle(case, row_chunk=256)
+    mod = util.make_module(case, torch.float32)
+    out = util.run_module(mod, case, torch.float32)
+    util.assert_close(out[0], want[0], atol=2e-5, rtol=1e-4, what="c3 feats")
+    util.assert_close(out[1], want[1], atol=2e-5, rtol=1e-4, what="c3 coors")
+    m64 = util.make_module(case, torch.float64)
+    o64 = util.run_module(m64, case, torch.float64)
+    util.assert_close(o64[0], want[0], atol=1e-9, rtol=1e-9, what="c3 feats fp64")
+    util.assert_close(o64[1], want[1], atol=1e-9, rtol=1e-9, what="c3 coors fp64")
+
+
+# ------------------------------------------------------------------ c4: EGNN(dim=256, edge_dim=4), k=32, N=4096 (2 of the 64 graphs)
+def test_c4_two_graphs_row_block_vs_oracle_and_equivariance():
+    B, N = 2, 4096
+    spec = dict(kind="layer", cfg=dict(dim=256, edge_dim=4, num_nearest_neighbors=32), B=B, N=N, seed=4)
+    case = cases.build_case(spec)
+    mod = util.make_module(case, torch.float32)
+    ins = case["inputs"]
+    feats = util.to_torch(ins["feats"], torch.float32, "cuda")
+    coors = util.to_torch(ins["coors"], torch.float32, "cuda")
+    edges = util.to_torch(ins["edges"], torch.float32, "cuda")
+    f, x = mod(feats, coors, edges)
+    # neighbour selection is done in fp32 on the GPU: feed the oracle fp32-rounded coordinates so both rank the same values
+    c32 = ins["coors"].astype(np.float32).astype(np.float64)
+    wf, wx = cases.O.egnn_layer_forward(case["params"], case["cfg"], ins["feats"][1:2], c32[1:2], edges=ins["edges"][1:2],
+                                        rows=(1000, 1064))
+    util.assert_close(f[1:2, 1000:1064], wf, atol=2e-5, rtol=1e-4, what="c4 feats rows")
+    util.assert_close(x[1:2, 1000:1064], wx, atol=2e-5, rtol=1e-4, what="c4 coors rows")
+    q, t = rotation(4)
+    fr, xr = mod(feats, (coors.double().cpu() @ q + t).float().cuda(), edges)
+    assert float((fr - f).abs().max()) < 1e-5 * float(f.abs().max()) + 1e-6
+    assert float((xr.double().cpu() - (x.double().cpu() @ q + t)).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------ c5: EGNN_Network only_sparse, 3 adjacency degrees, chain, N=8192
+def test_c5_full_size_properties_and_reduced_size_values():
+    from egnn_pytorch_b200 import EGNN_Network
+    N = 8192
+    torch.manual_seed(0)
+    net = EGNN_Network(num_tokens=21, dim=32, depth=3, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True).cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randint(0, 21, (1, N), generator=g).cuda()
+    coors = torch.randn(1, N, 3, generator=g).cuda()
+    mask = torch.ones(1, N, dtype=torch.bool).cuda()
+    i = torch.arange(N)
+    adj = ((i[:, None] - i[None, :]).abs() <= 1).cuda()               # README.md:89-90 chain with diagonal
+    f, x = net(feats, coors, adj_mat=adj, mask=mask)
+    assert torch.isfinite(f).all() and torch.isfinite(x).all()
+    # the expanded chain reaches +-4 hops: a node's output depends on exactly that window
+    feats2 = feats.clone(); feats2[0, 5000] = (feats2[0, 5000] + 1) % 21
+    f2, x2 = net(feats2, coors, adj_mat=adj, mask=mask)
+    changed = ((f2 - f).abs().amax(-1) > 0)[0].nonzero().flatten().cpu()
+    assert int(changed.min()) >= 5000 - 12 and int(changed.max()) <= 5000 + 12      # 3 layers x 4 hops
+    assert 5000 in changed.tolist()
+    q, t = rotation(6)
+    fr, xr = net(feats, (coors.double().cpu() @ q + t).float().cuda(), adj_mat=adj, mask=mask)
+    assert float((fr - f).abs().max()) < 1e-5
+    assert float((xr.double().cpu() - (x.double().cpu() @ q + t)).abs().max()) < 1e-5
+    # values at N=512 against the oracle (same network hyper-parameters)
+    spec = dict(kind="network", cfg=dict(depth=3, dim=32, num_tokens=21, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True),
+                B=1, N=512, seed=5, adj="chain", mask="full")
+    case = cases.build_case(spec)
+    want = cases.run_oracle(case, row_chunk=128)
+    mod = util.make_module(case, torch.float32)
+    out = util.run_module(mod, case, torch.float32)
+    util.assert_close(out[0], want[0], atol=2e-5, rtol=1e-4, what="c5@512 feats")
+    util.assert_close(out[1], want[1], atol=2e-5, rtol=1e-4, what="c5@512 coors")

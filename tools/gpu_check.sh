@@ -28,3 +28,6 @@ if [ "${EAGER:-0}" = "1" ]; then
 timeout 600 python bench.py --impl eager --dtype bf16 --steps 5 --warmup 2 > gpurun_out/eager_bf16.json 2> gpurun_out/eager_bf16.err; cat gpurun_out/eager_bf16.json; tail -3 gpurun_out/eager_bf16.err
 timeout 600 python bench.py --impl eager --dtype fp32 --steps 3 --warmup 1 > gpurun_out/eager_fp32.json 2> gpurun_out/eager_fp32.err; cat gpurun_out/eager_fp32.json; tail -3 gpurun_out/eager_fp32.err
 fi
+if [ "${CONFIGS:-0}" = "1" ]; then
+timeout 900 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err; cat gpurun_out/configs.jsonl; tail -3 gpurun_out/configs.err
+fi
