@@ -75,6 +75,12 @@ template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return fma(a, b, c); }
 
+// a*a + acc WITHOUT fma contraction: the reference forms (rel ** 2).sum(-1) (egnn_pytorch.py:233) with separate
+// multiplies and adds, and neighbour ranking is sensitive to the last bit near the k-th boundary.
+template <typename T> __device__ __forceinline__ T sq_acc(T a, T acc);
+template <> __device__ __forceinline__ float sq_acc<float>(float a, float acc) { return __fadd_rn(acc, __fmul_rn(a, a)); }
+template <> __device__ __forceinline__ double sq_acc<double>(double a, double acc) { return __dadd_rn(acc, __dmul_rn(a, a)); }
+
 // 4 consecutive elements, 4-element aligned.
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {

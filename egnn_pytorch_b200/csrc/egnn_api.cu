@@ -66,7 +66,13 @@ template <typename T, int MP, bool KNN>
 static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
   const size_t smem = pair_smem_bytes<T>(a.s, a.L, KNN);
   if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
-  EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_kernel<T, MP, KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_set[64] = {0};                 // per device: largest dynamic-smem size already opted in
+  int dev = 0;
+  EGNN_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && smem_set[dev] < smem) {
+    EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_kernel<T, MP, KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[dev] = smem;
+  }
   const int TI = PAIR_THREADS / a.TS;
   dim3 grid(ceil_div(a.s.row1 - a.s.row0, TI), a.s.B);
   pair_kernel<T, MP, KNN><<<grid, PAIR_THREADS, smem, st>>>(a);

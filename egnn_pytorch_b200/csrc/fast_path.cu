@@ -168,10 +168,12 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
 }
 
 int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  EGNN_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
     EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid(ceil_div(g.Nout, GEMM_BN), ceil_div(g.M, GEMM_BM));
   tc_gemm_kernel<<<grid, 128, GEMM_SMEM_BYTES, st>>>(g);
@@ -259,7 +261,13 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     a.m_out = uf ? node_in + s.dim : nullptr;
     a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
     const size_t smem = tc_pair_smem_bytes(f.Hp);
-    EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set[64] = {0};
+    int dev = 0;
+    EGNN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && smem_set[dev] < smem) {
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[dev] = smem;
+    }
     dim3 grid(ceil_div(s.N, TP_TI), s.B);
     tc_pair_kernel<<<grid, TP_THREADS, smem, st>>>(a);
     EGNN_LAUNCH_CHECK();

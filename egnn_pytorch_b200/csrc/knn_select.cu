@@ -32,7 +32,7 @@ template <typename T>
 __device__ __forceinline__ T rank_of(const SelArgs<T>& a, int b, int i, int j, const T* xi, bool mask_i) {
   const T* xj = a.coors + ((size_t)b * a.N + j) * a.C;
   T d = T(0);
-  for (int c = 0; c < a.C; ++c) { T r = xi[c] - xj[c]; d += r * r; }
+  for (int c = 0; c < a.C; ++c) d = sq_acc<T>(xi[c] - xj[c], d);
   if (a.mask && !(mask_i && a.mask[(size_t)b * a.N + j])) d = T(1e5);
   if (a.adj) {
     if (i == j) d = T(-1);

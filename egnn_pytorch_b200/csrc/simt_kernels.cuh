@@ -277,7 +277,7 @@ pair_kernel(const PairArgs<T> a) {
 #pragma unroll
       for (int c = 0; c < PAIR_CMAX; ++c) {
         rel[c] = T(0);
-        if (c < s.C) { rel[c] = xi[c] - xj[c]; d += rel[c] * rel[c]; }
+        if (c < s.C) { rel[c] = xi[c] - xj[c]; d = sq_acc<T>(rel[c], d); }
       }
     }
     // ---- per-pair scalar channels other than d go through shared memory
