@@ -141,6 +141,49 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
 }
 
 // =====================================================================================
+// Same contract as gemm_nt_kernel for few rows (Mr <= 16, the latency-bound configs c1/README example):
+// one warp per output column n reads W[n, :] once, coalesced, and keeps all Mr row sums in registers.
+// =====================================================================================
+template <typename T, int ACT, bool RES>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
+                   const T* __restrict__ bias, const T* __restrict__ R, int ldr,
+                   T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map) {
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (col >= Nout) return;
+  T acc[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = T(0);
+  if (col < Nv) {
+    const T* w = W + (size_t)col * ldw;
+    for (int k = lane; k < K; k += 32) {
+      const T wv = w[k];
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if (m < Mr) acc[m] = fma_t(A[map(m) * lda + k], wv, acc[m]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[m] += shfl_xor_t<T>(acc[m], o);
+  if (lane < Mr) {
+    T v = T(0);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) if (m == lane) v = acc[m];
+    const size_t row = map(lane);
+    if (col < Nv) {
+      v += bias ? bias[col] : T(0);
+      if (ACT == 1) v = silu_acc<T>(v);
+      if (RES) v += R[row * ldr + col];
+    } else {
+      v = T(0);
+    }
+    Cout[row * ldo + col] = v;
+  }
+}
+
+// =====================================================================================
 // node_in[row, 0:dim] = LayerNorm(h[row]) or h[row]   (egnn_pytorch.py:335); one warp per row.
 // =====================================================================================
 template <typename T>

@@ -22,8 +22,8 @@ Forward only in this round: outputs carry no autograd graph (SURVEY.md section 8
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
-import math
 import os
 
 import torch
@@ -133,22 +133,29 @@ class EGNN(nn.Module):
 
     # -------------------------------------------------------------- parameter staging
     def _state_fields(self):
-        out = {}
-        for key, p in self.named_parameters():
-            f = nat.STATE_KEY_TO_FIELD.get(key)
-            if f is not None:
-                out[f] = p
-        return out
+        """[(EgnnLayerWeights field, Parameter)], cached; rebuilt if a Parameter object is replaced."""
+        cache = self.__dict__.get("_fields_cache")
+        if cache is not None and all(mod._parameters.get(name) is p for mod, name, _, p in cache):
+            return cache
+        cache = []
+        for mname, mod in self.named_modules():
+            for pname, p in mod._parameters.items():
+                key = f"{mname}.{pname}" if mname else pname
+                f = nat.STATE_KEY_TO_FIELD.get(key)
+                if f is not None and p is not None:
+                    cache.append((mod, pname, f, p))
+        self.__dict__["_fields_cache"] = cache
+        return cache
 
     def _staged(self, device, dtype):
         fields = self._state_fields()
-        sig = tuple((n, p.data_ptr(), p._version, p.dtype, str(p.device)) for n, p in fields.items())
-        key = (str(device), dtype)
+        sig = tuple((p.data_ptr(), p._version) for _, _, _, p in fields)
+        key = (device, dtype)
         st = self._stage.get(key)
         if st is None or st["sig"] != sig:
             with torch.no_grad():
-                tensors = {n: p.detach().to(device=device, dtype=dtype).contiguous() for n, p in fields.items()}
-            st = dict(sig=sig, tensors=tensors, packed={})
+                tensors = {f: p.detach().to(device=device, dtype=dtype).contiguous() for _, _, f, p in fields}
+            st = dict(sig=sig, tensors=tensors, packed={}, wstruct={})
             self._stage[key] = st
         return st
 
@@ -221,7 +228,12 @@ class EGNN(nn.Module):
         T = dict(st["tensors"])
         lab_w = None
         if label_emb is not None:
-            lab_w = label_emb.detach().to(device=dev, dtype=kdt).contiguous()
+            lab_w = st.get("lab_keepalive")
+            if lab_w is None or st.get("lab_sig") != (label_emb.data_ptr(), label_emb._version):
+                lab_w = label_emb.detach().to(device=dev, dtype=kdt).contiguous()
+                st["lab_sig"] = (label_emb.data_ptr(), label_emb._version)
+                st["wstruct"] = {}
+                st["packed"] = {}
             T["label_emb"] = lab_w
 
         desc = nat.LayerDesc(
@@ -230,10 +242,16 @@ class EGNN(nn.Module):
             m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
             valid_radius=float(self.valid_radius), clamp=float(self.coor_weights_clamp_value or 0.0),
             row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0)
-        w = nat.LayerWeights(**{f: (T[f].data_ptr() if f in T else None) for f in nat.WEIGHT_FIELDS})
+        wkey = None if lab_w is None else (label_emb.data_ptr(), label_emb._version)
+        w = st["wstruct"].get(wkey)
+        if w is None:
+            w = nat.LayerWeights(**{f: (T[f].data_ptr() if f in T else None) for f in nat.WEIGHT_FIELDS})
+            st["wstruct"] = {wkey: w}
+            st["lab_keepalive"] = lab_w
 
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        with torch.cuda.device(dev):
+        ctx = contextlib.nullcontext() if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+        with ctx:
             # packed parameters, cached until a parameter changes
             pkey = (label_dim, 0 if lab_w is None else (label_emb.data_ptr(), label_emb._version))
             packed = st["packed"].get(pkey)
