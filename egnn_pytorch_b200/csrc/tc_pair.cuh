@@ -213,26 +213,32 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
 #pragma unroll
           for (int rho = 0; rho < 4; ++rho) dr[rho] = dwg[i * TP_JB + wq * 32 + lr + 8 * rho];
           const float* Ai = As + (size_t)i * Hp + c * TP_KC + lq * 4;
+          float4 avr[4];
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) avr[sl] = *reinterpret_cast<const float4*>(Ai + sl * 16);
           const uint32_t ta = tm_wg + TP_TI * 16 + slot * 32;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {       // rows (lr, lr+8), then (lr+16, lr+24)
             uint32_t hp[16];
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) {
-              const float4 av = *reinterpret_cast<const float4*>(Ai + sl * 16);
+              const float4 av = avr[sl];
               const float4 wv = wdr[sl];
 #pragma unroll
               for (int r2 = 0; r2 < 2; ++r2) {
                 const int rho = half * 2 + r2;
                 const uint2 bb = Bc[rho][sl];
                 const float d = dr[rho];
-                const float y0 = tc::add_bf16_lo(bb.x, fmaf(wv.x, d, av.x));
-                const float y1 = tc::add_bf16_hi(bb.x, fmaf(wv.y, d, av.y));
-                const float y2 = tc::add_bf16_lo(bb.y, fmaf(wv.z, d, av.z));
-                const float y3 = tc::add_bf16_hi(bb.y, fmaf(wv.w, d, av.w));
+                const float2 dd = make_float2(d, d);
+                const float2 z01 = tc::ffma2(make_float2(wv.x, wv.y), dd, make_float2(av.x, av.y));   // wd*d + A'
+                const float2 z23 = tc::ffma2(make_float2(wv.z, wv.w), dd, make_float2(av.z, av.w));
+                const float2 y01 = make_float2(tc::add_bf16_lo(bb.x, z01.x), tc::add_bf16_hi(bb.x, z01.y));  // + B'
+                const float2 y23 = make_float2(tc::add_bf16_lo(bb.y, z23.x), tc::add_bf16_hi(bb.y, z23.y));
+                const float2 h01 = tc::ffma2(y01, make_float2(tc::tanh_fast(y01.x), tc::tanh_fast(y01.y)), y01);  // y + y tanh y
+                const float2 h23 = tc::ffma2(y23, make_float2(tc::tanh_fast(y23.x), tc::tanh_fast(y23.y)), y23);
                 // 16x256b fragment: regs {0,1} of a slab -> row lr (+16), regs {2,3} -> row lr+8 (+24); even k low
-                hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
-                hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
+                hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(h01.x, h01.y);
+                hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(h23.x, h23.y);
                 if (reload) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
               }
             }

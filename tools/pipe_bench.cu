@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(1024) k(float* out, int iters, float seed) {
       if (OP == 3) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(u[i]));
       if (OP == 4) asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
       if (OP == 5) asm volatile("fma.rn.bf16x2 %0, %0, %1, %0;" : "+r"(u[i]) : "r"(0x3f803f80u));
+      if (OP == 7) { unsigned long long r = ((unsigned long long)u[i] << 32) | u[(i + 1) & 7];
+                     asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(r) : "l"(0x3f8000003f800000ull));
+                     u[i] = (uint32_t)(r >> 32); }
       if (OP == 6) { asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));            // mixed: 1 MUFU + 3 FMA
                      asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
                      asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
@@ -59,5 +62,6 @@ int main() {
   run<4>("fma.f32", 1, sms);
   run<5>("fma.bf16x2 (x2)", 2, sms);
   run<6>("tanh.f32 + 3 fma (per tanh)", 1, sms);
+  run<7>("fma.f32x2 (x2, +2 int ops)", 2, sms);
   return 0;
 }
