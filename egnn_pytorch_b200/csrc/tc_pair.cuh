@@ -267,47 +267,60 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
       tc::tc_fence_after();
       const float* W3 = epi; const float* b3 = epi + 1024; const float* w4 = b3 + 64;
       const float* b2 = w4 + 64; const float* gw = b2 + 16; const float* sc = gw + 16;   // sc: gate_b, b4, scale
-#pragma unroll 1
+      float m[TP_TI][16];                              // m_ij of this thread's pair for the TI rows
+#pragma unroll
       for (int i = 0; i < TP_TI; ++i) {
         uint32_t r[16];
         tc::tmem_ld16(tm_wg + i * 16, r);
         tc::tmem_wait_ld();
-        float m[16];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) m[o] = tc::silu_half_arg(0.5f * (__uint_as_float(r[o]) + b2[o]));    // :183
-        if (a.flags & EGNN_FLAG_SOFT_EDGES) {                                                             // :289-290
+        for (int o = 0; o < 16; ++o) m[i][o] = tc::silu_half_arg(0.5f * (__uint_as_float(r[o]) + b2[o]));    // :183
+        if (a.flags & EGNN_FLAG_SOFT_EDGES) {                                                               // :289-290
           float z = sc[0];
 #pragma unroll
-          for (int o = 0; o < 16; ++o) z = fmaf(gw[o], m[o], z);
+          for (int o = 0; o < 16; ++o) z = fmaf(gw[o], m[i][o], z);
           const float gate = 0.5f + 0.5f * tc::tanh_fast(0.5f * z);
 #pragma unroll
-          for (int o = 0; o < 16; ++o) m[o] *= gate;
+          for (int o = 0; o < 16; ++o) m[i][o] *= gate;
         }
-        const bool pm = jv && (mki[i] != 0) && (a.has_mask ? mask_j : true);
-        float v[20];
-        float w = 0.f;
-        if (upd_coors) {                                                                                  // :302-315
-          w = sc[1];
-#pragma unroll 4
-          for (int u = 0; u < 64; ++u) {
-            const float4* w3 = reinterpret_cast<const float4*>(W3 + u * 16);
-            float tt = b3[u];
+      }
+      float wgt[TP_TI];
 #pragma unroll
-            for (int o4 = 0; o4 < 4; ++o4) {
-              const float4 ww = w3[o4];
-              tt = fmaf(ww.x, m[o4 * 4], tt); tt = fmaf(ww.y, m[o4 * 4 + 1], tt);
-              tt = fmaf(ww.z, m[o4 * 4 + 2], tt); tt = fmaf(ww.w, m[o4 * 4 + 3], tt);
-            }
-            w = fmaf(w4[u], tc::silu_half_arg(0.5f * tt), w);
+      for (int i = 0; i < TP_TI; ++i) wgt[i] = 0.f;
+      if (upd_coors) {                                                                                      // :302-315
+#pragma unroll
+        for (int i = 0; i < TP_TI; ++i) wgt[i] = sc[1];
+        // hidden unit u outermost: one W3 row (4 x LDS.128) serves all TI rows of this pair
+#pragma unroll 2
+        for (int u = 0; u < 64; ++u) {
+          const float4* w3 = reinterpret_cast<const float4*>(W3 + u * 16);
+          const float4 wa = w3[0], wb = w3[1], wc = w3[2], wd4 = w3[3];
+          const float bu = b3[u], w4u = w4[u];
+#pragma unroll
+          for (int i = 0; i < TP_TI; ++i) {
+            float tt = bu;
+            tt = fmaf(wa.x, m[i][0], tt); tt = fmaf(wa.y, m[i][1], tt); tt = fmaf(wa.z, m[i][2], tt); tt = fmaf(wa.w, m[i][3], tt);
+            tt = fmaf(wb.x, m[i][4], tt); tt = fmaf(wb.y, m[i][5], tt); tt = fmaf(wb.z, m[i][6], tt); tt = fmaf(wb.w, m[i][7], tt);
+            tt = fmaf(wc.x, m[i][8], tt); tt = fmaf(wc.y, m[i][9], tt); tt = fmaf(wc.z, m[i][10], tt); tt = fmaf(wc.w, m[i][11], tt);
+            tt = fmaf(wd4.x, m[i][12], tt); tt = fmaf(wd4.y, m[i][13], tt); tt = fmaf(wd4.z, m[i][14], tt); tt = fmaf(wd4.w, m[i][15], tt);
+            wgt[i] = fmaf(w4u, tc::silu_half_arg(0.5f * tt), wgt[i]);
           }
-          if (!pm) w = 0.f;                                                                               // :309
-          if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);                          // :313
-          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dwg[i * TP_JB + t128]), 1e-8f);    // :74-77
         }
+      }
+#pragma unroll
+      for (int i = 0; i < TP_TI; ++i) {
+        const bool pm = jv && (mki[i] != 0) && (a.has_mask ? mask_j : true);
+        float w = wgt[i];
+        if (upd_coors) {
+          if (!pm) w = 0.f;                                                                                 // :309
+          if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);                            // :313
+          if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dwg[i * TP_JB + t128]), 1e-8f);      // :74-77
+        }
+        float v[20];
         v[16] = w * (xis[i * 4 + 0] - xj0); v[17] = w * (xis[i * 4 + 1] - xj1); v[18] = w * (xis[i * 4 + 2] - xj2);
         v[19] = pm ? 1.f : 0.f;
 #pragma unroll
-        for (int o = 0; o < 16; ++o) v[o] = pm ? m[o] : 0.f;                                              // :322
+        for (int o = 0; o < 16; ++o) v[o] = pm ? m[i][o] : 0.f;                                             // :322
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
