@@ -7,8 +7,13 @@
 #include "profile.h"
 #include "tc_gemm.cuh"
 #include "tc_pair.cuh"
+#include "tc_knn.cuh"
 
 namespace egnn {
+
+int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
+                        const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
+                        uint8_t* out_ok, cudaStream_t st);
 
 namespace {
 
@@ -20,7 +25,7 @@ struct FastDims {
 
 // layout of the packed-parameter buffer (byte offsets, 256-aligned)
 struct FastPack {
-  size_t w1i, w1j, b1, wdh, w2p, epi, wn1, bn1, wn2, bn2, lng, lnb, total;
+  size_t w1i, w1j, b1, wdh, weh, w2p, epi, wn1, bn1, wn2, bn2, lng, lnb, total;
 };
 
 FastDims fast_dims(const EgnnLayerDesc& d) {
@@ -40,6 +45,7 @@ FastPack fast_pack_layout(const FastDims& f) {
   p.w1j = take((size_t)f.Hp * d * 2);
   p.b1 = take((size_t)f.Hp * 4);
   p.wdh = take((size_t)f.Hp * 4);
+  p.weh = take((size_t)TK_QE * f.Hp * 4);
   p.w2p = take((size_t)f.Hp * 32);
   p.epi = take((size_t)TP_EPI_FLOATS * 4);
   p.wn1 = take((size_t)2 * d * f.Kn * 2);
@@ -54,12 +60,17 @@ FastPack fast_pack_layout(const FastDims& f) {
 
 int fast_supported(const EgnnLayerDesc& d) {
   const FastDims f = fast_dims(d);
-  if (d.k != 0) return EGNN_ERR_UNSUPPORTED;                       // dense all-pairs only (this round)
-  if (d.edge_dim != 0 || d.label_dim != 0 || d.fourier != 0) return EGNN_ERR_UNSUPPORTED;
+  if (d.label_dim != 0 || d.fourier != 0) return EGNN_ERR_UNSUPPORTED;
+  if (d.k == 0) {                                                  // dense all-pairs: tc_pair_kernel
+    if (d.edge_dim != 0) return EGNN_ERR_UNSUPPORTED;
+    if (tc_pair_smem_bytes(f.Hp) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
+  } else {                                                         // neighbour lists: tc_knn_kernel
+    if (d.k > 32 || d.edge_dim > TK_QE) return EGNN_ERR_UNSUPPORTED;
+    if (tc_knn_smem_bytes(f.Hp, d.edge_dim > 0) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
+  }
   if (d.C != 3 || d.m_dim != 16) return EGNN_ERR_UNSUPPORTED;
   if (d.dim % 8 != 0) return EGNN_ERR_UNSUPPORTED;                 // 16-byte rows for cp.async
   if (!(d.row_begin == 0 && (d.row_end == 0 || d.row_end == d.N))) return EGNN_ERR_UNSUPPORTED;
-  if (tc_pair_smem_bytes(f.Hp) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
   return EGNN_OK;
 }
 
@@ -82,6 +93,12 @@ __global__ void fast_pack_kernel(FastDims f, FastPack L, EgnnLayerWeights w, uin
   for (size_t c = t0; c < (size_t)Hp; c += stride) {
     b1[c] = c < (size_t)H ? bf(w.edge_b1, c) : 0.f;
     wdh[c] = c < (size_t)H ? 0.5f * bf(w.edge_w1, c * E + 2 * d) : 0.f;      // the d_ij column of W1, pre-halved
+  }
+  float* weh = reinterpret_cast<float*>(out + L.weh);                          // continuous edge columns, pre-halved
+  for (size_t x = t0; x < (size_t)TK_QE * Hp; x += stride) {
+    const int q = (int)(x / Hp);
+    const size_t c = x % Hp;
+    weh[x] = (c < (size_t)H && q < s.edge_dim) ? 0.5f * bf(w.edge_w1, c * E + 2 * d + 1 + q) : 0.f;
   }
   // W2 [16][H] -> UMMA K-major core matrices: [slab = c/16][kc = (c%16)/8][nc = n/8][r = n%8][e = c%8]
   __nv_bfloat16* w2p = reinterpret_cast<__nv_bfloat16*>(out + L.w2p);
@@ -153,7 +170,7 @@ __global__ void ln_concat_bf16_kernel(const __nv_bfloat16* __restrict__ h, const
   for (int c = lane; c < dim; c += 32) y[c] = __float2bfloat16((__bfloat162float(x[c]) - mu) * rstd * g[c] + bta[c]);
 }
 
-struct FastWs { size_t Atab, Btab, node_in, h1, total; };
+struct FastWs { size_t Atab, Btab, node_in, h1, nbr_idx, nbr_ok, total; };
 FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   FastWs w;
   size_t o = 0;
@@ -163,6 +180,8 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   w.Btab = take((size_t)f.s.M * f.Hp * 2);
   w.node_in = take(uf ? (size_t)f.s.M * f.Kn * 2 : 0);
   w.h1 = take(uf ? (size_t)f.s.M * 2 * f.s.dim * 2 : 0);
+  w.nbr_idx = take((size_t)f.s.M * f.s.k * sizeof(int32_t));
+  w.nbr_ok = take((size_t)f.s.M * f.s.k);
   w.total = o;
   return w;
 }
@@ -247,7 +266,7 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     g.out = Btab; g.out_f32 = 0;
     EGNN_TRY(launch_tc_gemm(g, st));
   }
-  {  // fused edge kernel
+  if (s.k == 0) {  // fused edge kernel, dense all-pairs
     StageTimer tm(st, STAGE_PAIR);
     TcPairArgs a{};
     a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim;
@@ -270,6 +289,46 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     }
     dim3 grid(ceil_div(s.N, TP_TI), s.B);
     tc_pair_kernel<<<grid, TP_THREADS, smem, st>>>(a);
+    EGNN_LAUNCH_CHECK();
+    count_launch();
+  } else {         // neighbour lists: distance + top-k select, then the gathered fused edge kernel
+    int32_t* nbr_idx = reinterpret_cast<int32_t*>(base + wl.nbr_idx);
+    uint8_t* nbr_ok = base + wl.nbr_ok;
+    {
+      StageTimer tm(st, STAGE_SELECT);
+      const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;
+      EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, 3, s.k, io.coors, io.mask, io.adj,
+                                   (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
+      count_launch();
+    }
+    StageTimer tm(st, STAGE_PAIR);
+    TcKnnArgs a{};
+    a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim; a.k = s.k; a.edge_dim = s.edge_dim;
+    a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp;
+    a.Atab = Atab; a.Btab = Btab;
+    a.wdh = reinterpret_cast<const float*>(pk + L.wdh);
+    a.weh = reinterpret_cast<const float*>(pk + L.weh);
+    a.w2p = reinterpret_cast<const __nv_bfloat16*>(pk + L.w2p);
+    a.epi = reinterpret_cast<const float*>(pk + L.epi);
+    a.coors = static_cast<const float*>(io.coors);
+    a.edges = static_cast<const __nv_bfloat16*>(io.edges);
+    a.mask = io.mask;
+    a.nbr_idx = nbr_idx; a.nbr_ok = nbr_ok;
+    a.m_out = uf ? node_in + s.dim : nullptr;
+    a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
+    const bool ed = s.edge_dim > 0;
+    const size_t smem = tc_knn_smem_bytes(f.Hp, ed);
+    static size_t smem_set[2][64] = {{0}};
+    int dev = 0;
+    EGNN_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && smem_set[ed][dev] < smem) {
+      if (ed) EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_knn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      else EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[ed][dev] = smem;
+    }
+    dim3 grid(ceil_div(s.N, TK_ROWS), s.B);
+    if (ed) tc_knn_kernel<true><<<grid, TK_THREADS, smem, st>>>(a);
+    else tc_knn_kernel<false><<<grid, TK_THREADS, smem, st>>>(a);
     EGNN_LAUNCH_CHECK();
     count_launch();
   }

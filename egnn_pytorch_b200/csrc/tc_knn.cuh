@@ -1,0 +1,308 @@
+// The fused edge step on tensor cores for neighbour lists (k <= 32 neighbours per node, bf16 operands).
+//
+// Reference semantics: the use_nearest branch of EGNN.forward -- gathers of rel_coors / rel_dist / edges / feats
+// along the selected neighbours (egnn_pytorch.py:262-266, :275), edge MLP (:287), gate (:289-290), neighbour
+// mask incl. valid_radius (:292-300), coors MLP / clamp / CoorsNorm (:302-315), pooling (:319-333).  The
+// neighbour lists come from egnn_knn_select (knn_select.cu).
+//
+// Same machinery as tc_pair.cuh (hidden values produced in fp32 registers, stored as the bf16 A operand into
+// TMEM with tcgen05.st.16x256b, tcgen05.mma M=128 N=16 K=16 against the W2 slab in shared memory, accumulators
+// in TMEM, issue duty rotating over the warps of a warpgroup and deferred by half a round).  What differs:
+//   * one WARP owns one query row i and its 32 neighbour slots (slot >= k is padding), so a warpgroup's 128
+//     MMA rows are 4 query rows x 32 slots and the reduction over j is a single warp shuffle tree;
+//   * the B' row of every pair is gathered from L2 (8-byte pieces, contiguous across the 4 lanes that share a
+//     pair) and used once: each 64-channel round re-fills its B' registers for the next chunk right after use;
+//   * up to 4 continuous edge channels per pair are folded in on the CUDA cores (We from shared memory).
+#pragma once
+
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_pair.cuh"     // TP_EPI_FLOATS and the epilogue constant layout
+
+namespace egnn {
+
+constexpr int TK_ROWS = 16;        // query rows per CTA (one per warp)
+constexpr int TK_KC = 64;
+constexpr int TK_SLOTS = 3;
+constexpr int TK_THREADS = 512;
+constexpr int TK_WGCOLS = 128;     // 16 accumulator + 3 x 32 operand columns (+16 spare)
+constexpr int TK_QE = 4;           // edge channels folded per pair (edge_dim <= 4, zero padded)
+
+struct TcKnnArgs {
+  int B, N, Hp, ldn, dim, k, edge_dim;
+  uint32_t flags; int has_mask; float clamp;
+  const float* Atab;               // [M][Hp]  0.5 (h W1_i^T + b1)
+  const __nv_bfloat16* Btab;       // [M][Hp]  0.5 h W1_j^T
+  const float* wdh;                // [Hp]     0.5 W1[:, 2dim]
+  const float* weh;                // [TK_QE][Hp]  0.5 W1[:, 2dim+1+q]  (zero rows beyond edge_dim)
+  const __nv_bfloat16* w2p;        // W2 in core-matrix order
+  const float* epi;
+  const float* coors;              // [B][N][3]
+  const __nv_bfloat16* edges;      // [B][N][N][edge_dim] | null
+  const uint8_t* mask;             // [B][N] | null
+  const int32_t* nbr_idx;          // [B][N][k]
+  const uint8_t* nbr_ok;           // [B][N][k]
+  __nv_bfloat16* m_out;            // node_in + dim (stride ldn) | null
+  float* coors_out;                // [B][N][3] | null
+};
+
+inline size_t tc_knn_smem_bytes(int Hp, bool has_edges) {
+  size_t n = 0;
+  n += (size_t)Hp * 32;                       // W2 slabs
+  n += (size_t)TK_ROWS * Hp * 4;              // A rows (fp32)
+  n += (size_t)Hp * 4;                        // wd
+  n += has_edges ? (size_t)TK_QE * Hp * 4 : 0;   // We
+  n += (size_t)TP_EPI_FLOATS * 4;             // epilogue constants
+  n += 64 + 32 * 8;                           // tmem pointer, mbarriers
+  return n + 128;
+}
+
+template <bool EDGES>
+__global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  const int Hp = a.Hp, N = a.N, K = a.k;
+  unsigned char* w2s = sm;
+  float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [16][Hp]
+  float* wds = As + (size_t)TK_ROWS * Hp;                                     // [Hp]
+  float* wes = wds + Hp;                                                      // [QE][Hp] (EDGES only)
+  float* epi = wes + (EDGES ? TK_QE * Hp : 0);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(epi + TP_EPI_FLOATS);          // [0] tmem pointer
+  uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 16);
+  uint64_t* full = bars;                      // [4][SLOTS]
+  uint64_t* empty = bars + 4 * TK_SLOTS;      // [4][SLOTS]
+  uint64_t* accdone = empty + 4 * TK_SLOTS;   // [4]
+  uint64_t* ldbar = accdone + 4;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i0 = blockIdx.x * TK_ROWS;
+  const int rows_valid = min(TK_ROWS, N - i0);
+  const int nchunks = Hp / TK_KC;
+  const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
+
+  if (tid == 0) {
+    for (int x = 0; x < 4 * TK_SLOTS; ++x) { tc::mbar_init(&full[x], 128); tc::mbar_init(&empty[x], 1); }
+    for (int x = 0; x < 4; ++x) tc::mbar_init(&accdone[x], 1);
+    tc::mbar_init(ldbar, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(&misc[0]);
+  for (int x = tid; x < TP_EPI_FLOATS; x += TK_THREADS) epi[x] = a.epi[x];
+  for (int x = tid + rows_valid * Hp; x < TK_ROWS * Hp; x += TK_THREADS) As[x] = 0.f;
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = misc[0];
+
+  if (tid == 0) {
+    const uint32_t w2_bytes = (uint32_t)Hp * 32, as_bytes = (uint32_t)rows_valid * Hp * 4, wd_bytes = (uint32_t)Hp * 4;
+    const uint32_t we_bytes = EDGES ? (uint32_t)TK_QE * Hp * 4 : 0u;
+    tc::mbar_arrive_expect_tx(ldbar, w2_bytes + as_bytes + wd_bytes + we_bytes);
+    auto bulk = [&](uint32_t dst, const unsigned char* src, uint32_t bytes) {
+      for (uint32_t o = 0; o < bytes; o += 16384) tc::tma_bulk_g2s(dst + o, src + o, min(16384u, bytes - o), ldbar);
+    };
+    bulk(tc::smem_u32(w2s), reinterpret_cast<const unsigned char*>(a.w2p), w2_bytes);
+    bulk(tc::smem_u32(As), reinterpret_cast<const unsigned char*>(a.Atab + ((size_t)b * N + i0) * Hp), as_bytes);
+    bulk(tc::smem_u32(wds), reinterpret_cast<const unsigned char*>(a.wdh), wd_bytes);
+    if (EDGES) bulk(tc::smem_u32(wes), reinterpret_cast<const unsigned char*>(a.weh), we_bytes);
+  }
+
+  const int g = warp >> 2, wq = warp & 3;
+  const int lr = lane >> 2, lq = lane & 3;
+  const uint32_t tm_wg = tmem + g * TK_WGCOLS + ((uint32_t)(wq * 32) << 16);
+  constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
+  const uint32_t w2a = tc::smem_u32(w2s);
+
+  // ---- this warp's query row
+  const bool iv = warp < rows_valid;
+  const int i = i0 + (iv ? warp : 0);
+  const size_t nodei = (size_t)b * N + i;
+  const float xi0 = a.coors[nodei * 3 + 0], xi1 = a.coors[nodei * 3 + 1], xi2 = a.coors[nodei * 3 + 2];
+  const bool mask_i = iv && (a.has_mask ? a.mask[nodei] != 0 : true);
+
+  // ---- pair mapping: lane = neighbour slot
+  const bool sv = iv && lane < K;
+  int j = i;
+  bool okj = true;
+  if (sv) {
+    j = a.nbr_idx[nodei * K + lane];
+    okj = a.nbr_ok[nodei * K + lane] != 0;
+  }
+  const size_t nodej = (size_t)b * N + j;
+  const float r0 = xi0 - a.coors[nodej * 3 + 0], r1 = xi1 - a.coors[nodej * 3 + 1], r2 = xi2 - a.coors[nodej * 3 + 2];
+  const float dmine = r0 * r0 + r1 * r1 + r2 * r2;
+  // ---- fragment mapping: rows (slots) lr + 8*rho of this warp; fetch their j, d, edges by shuffle / gather
+  int jf[4];
+  float dr[4];
+  float ef[4][TK_QE];
+#pragma unroll
+  for (int rho = 0; rho < 4; ++rho) {
+    jf[rho] = __shfl_sync(0xffffffffu, j, lr + 8 * rho);
+    dr[rho] = __shfl_sync(0xffffffffu, dmine, lr + 8 * rho);
+#pragma unroll
+    for (int q = 0; q < TK_QE; ++q) ef[rho][q] = 0.f;
+    if (EDGES) {
+      const __nv_bfloat16* ep = a.edges + (((size_t)b * N + i) * N + jf[rho]) * a.edge_dim;
+#pragma unroll
+      for (int q = 0; q < TK_QE; ++q) if (q < a.edge_dim) ef[rho][q] = __bfloat162float(ep[q]);
+    }
+  }
+  const uint2* Bp[4];
+#pragma unroll
+  for (int rho = 0; rho < 4; ++rho)
+    Bp[rho] = reinterpret_cast<const uint2*>(a.Btab + ((size_t)b * N + jf[rho]) * Hp + 4 * lq);
+
+  tc::mbar_wait(ldbar, 0);
+  uint2 Bc[4][4];
+#pragma unroll
+  for (int rho = 0; rho < 4; ++rho)
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = __ldg(Bp[rho] + sl * 4);
+
+  int pend_c = -1;
+  auto issue_pending = [&]() {
+    if (pend_c < 0) return;
+    const int pc = pend_c;
+    pend_c = -1;
+    if ((pc & 3) != wq) return;                       // rotating duty
+    const uint32_t pslot = (uint32_t)pc % TK_SLOTS;
+    tc::mbar_wait(&full[g * TK_SLOTS + pslot], ((uint32_t)pc / TK_SLOTS) & 1);
+    tc::tc_fence_after();
+    if (lane == 0) {
+      const uint32_t tm_g = tmem + g * TK_WGCOLS;
+#pragma unroll
+      for (int kk = 0; kk < TK_KC / 16; ++kk) {
+        const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(pc * 4 + kk) * 512, 256u, 128u);
+        tc::mma_ts(tm_g, tm_g + 16 + pslot * 32 + kk * 8, bd, IDESC, (pc > 0 || kk > 0) ? 1u : 0u);
+      }
+      tc::mma_commit(&empty[g * TK_SLOTS + pslot]);
+      if (pc + 1 == nchunks) tc::mma_commit(&accdone[g]);
+    }
+    __syncwarp();
+  };
+
+  const float* Arow = As + (size_t)warp * Hp + lq * 4;
+#pragma unroll 1
+  for (int c = 0; c < nchunks; ++c) {
+    const uint32_t slot = (uint32_t)c % TK_SLOTS;
+    const uint32_t ta = tm_wg + 16 + slot * 32;
+    const bool more = c + 1 < nchunks;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t hp[16];
+#pragma unroll
+      for (int sl = 0; sl < 4; ++sl) {
+        const float4 av = *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16);
+        const float4 wv = *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4);
+        float4 we[TK_QE];
+        if (EDGES) {
+#pragma unroll
+          for (int q = 0; q < TK_QE; ++q) we[q] = *reinterpret_cast<const float4*>(wes + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const int rho = half * 2 + r2;
+          const uint2 bb = Bc[rho][sl];
+          const float d = dr[rho];
+          float z0 = fmaf(wv.x, d, av.x), z1 = fmaf(wv.y, d, av.y), z2 = fmaf(wv.z, d, av.z), z3 = fmaf(wv.w, d, av.w);
+          if (EDGES) {
+#pragma unroll
+            for (int q = 0; q < TK_QE; ++q) {
+              const float e = ef[rho][q];
+              z0 = fmaf(we[q].x, e, z0); z1 = fmaf(we[q].y, e, z1); z2 = fmaf(we[q].z, e, z2); z3 = fmaf(we[q].w, e, z3);
+            }
+          }
+          const float y0 = tc::add_bf16_lo(bb.x, z0), y1 = tc::add_bf16_hi(bb.x, z1);
+          const float y2 = tc::add_bf16_lo(bb.y, z2), y3 = tc::add_bf16_hi(bb.y, z3);
+          hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
+          hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
+          if (more) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
+        }
+      }
+      if (half == 0) {
+        issue_pending();
+        tc::mbar_wait(&empty[g * TK_SLOTS + slot], (((uint32_t)c / TK_SLOTS) & 1) ^ 1);
+        tc::tc_fence_after();
+      }
+      tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
+    }
+    tc::tmem_wait_st();
+    tc::tc_fence_before();
+    tc::mbar_arrive(&full[g * TK_SLOTS + slot]);
+    pend_c = c;
+  }
+  issue_pending();
+
+  // ---- epilogue (pair mapping): one warp = one query row, shuffle tree over its 32 slots
+  tc::mbar_wait(&accdone[g], 0);
+  tc::tc_fence_after();
+  {
+    const float* W3 = epi; const float* b3 = epi + 1024; const float* w4 = b3 + 64;
+    const float* b2 = w4 + 64; const float* gw = b2 + 16; const float* sc = gw + 16;
+    uint32_t r[16];
+    tc::tmem_ld16(tm_wg, r);
+    tc::tmem_wait_ld();
+    float m[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) m[o] = tc::silu_half_arg(0.5f * (__uint_as_float(r[o]) + b2[o]));
+    if (a.flags & EGNN_FLAG_SOFT_EDGES) {
+      float z = sc[0];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) z = fmaf(gw[o], m[o], z);
+      const float gate = 0.5f + 0.5f * tc::tanh_fast(0.5f * z);
+#pragma unroll
+      for (int o = 0; o < 16; ++o) m[o] *= gate;
+    }
+    bool pm = sv;
+    if (a.has_mask) pm = pm && mask_i && (a.mask[nodej] != 0) && okj;      // :296-297 (nbhd_mask only with a mask)
+    float w = 0.f;
+    if (upd_coors) {
+      w = sc[1];
+#pragma unroll 4
+      for (int u = 0; u < 64; ++u) {
+        const float4* w3 = reinterpret_cast<const float4*>(W3 + u * 16);
+        float tt = b3[u];
+#pragma unroll
+        for (int o4 = 0; o4 < 4; ++o4) {
+          const float4 ww = w3[o4];
+          tt = fmaf(ww.x, m[o4 * 4], tt); tt = fmaf(ww.y, m[o4 * 4 + 1], tt);
+          tt = fmaf(ww.z, m[o4 * 4 + 2], tt); tt = fmaf(ww.w, m[o4 * 4 + 3], tt);
+        }
+        w = fmaf(w4[u], tc::silu_half_arg(0.5f * tt), w);
+      }
+      if (!pm) w = 0.f;
+      if (a.flags & EGNN_FLAG_CLAMP) w = fminf(fmaxf(w, -a.clamp), a.clamp);
+      if (!sv) w = 0.f;                                                  // padding slots carry nothing, clamp or not
+      if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dmine), 1e-8f);
+    }
+    float v[20];
+    v[16] = w * r0; v[17] = w * r1; v[18] = w * r2;
+    v[19] = pm ? 1.f : 0.f;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) v[o] = pm ? m[o] : 0.f;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+      for (int o = 0; o < 20; ++o) v[o] += __shfl_xor_sync(0xffffffffu, v[o], off);
+    if (iv) {
+      if (upd_feats && lane < 16) {
+        float inv = 1.f;
+        if (a.flags & EGNN_FLAG_POOL_MEAN) inv = a.has_mask ? (v[19] > 0.f ? 1.f / v[19] : 0.f) : 1.f / (float)K;
+        float mine = 0.f;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) if (o == lane) mine = v[o];
+        a.m_out[nodei * a.ldn + lane] = __float2bfloat16(mine * inv);
+      }
+      if (upd_coors && lane == 0) {
+        a.coors_out[nodei * 3 + 0] = xi0 + v[16];
+        a.coors_out[nodei * 3 + 1] = xi1 + v[17];
+        a.coors_out[nodei * 3 + 2] = xi2 + v[18];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace egnn

@@ -29,6 +29,21 @@ FAST_SPECS = {
     "d512_n256":       dict(kind=L, cfg=dict(dim=512), B=1, N=256, seed=91, init="xavier"),
     "d64_no_coors":    dict(kind=L, cfg=dict(dim=64, update_coors=False), B=1, N=40, seed=90, init="xavier"),
     "d64_no_feats":    dict(kind=L, cfg=dict(dim=64, update_feats=False), B=1, N=40, seed=89, init="xavier"),
+    # --- neighbour lists on the tensor-core path (tc_knn_kernel)
+    "knn_d64_k8":      dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=8), B=2, N=200, seed=80, init="xavier"),
+    "knn_d64_k32_e4":  dict(kind=L, cfg=dict(dim=64, edge_dim=4, num_nearest_neighbors=32), B=2, N=100, seed=81, init="xavier",
+                            mask="padded"),
+    "knn_d32_k5_e2":   dict(kind=L, cfg=dict(dim=32, edge_dim=2, num_nearest_neighbors=5, soft_edges=True, norm_coors=True,
+                                             coor_weights_clamp_value=1.0, m_pool_method="mean"), B=3, N=37, seed=82,
+                            init="xavier", mask="random"),
+    "knn_d64_radius":  dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=12, valid_radius=2.0), B=1, N=150, seed=83,
+                            init="xavier", mask="full"),
+    "knn_d256_c4":     dict(kind=L, cfg=dict(dim=256, edge_dim=4, num_nearest_neighbors=32), B=1, N=300, seed=84),
+    "knn_k_eq_n":      dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=20), B=2, N=20, seed=85, init="xavier"),
+    "adj_sparse_d64":  dict(kind=L, cfg=dict(dim=64, only_sparse_neighbors=True), B=2, N=50, seed=86, init="xavier", adj="chain",
+                            mask="full"),
+    "knn_mean_nomask": dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=7, m_pool_method="mean"), B=1, N=33, seed=87,
+                            init="xavier"),
 }
 
 
@@ -41,6 +56,8 @@ def run_fast(spec):
     case["params"] = {k: bf16_round(v) for k, v in case["params"].items()}
     case["inputs"]["feats"] = bf16_round(case["inputs"]["feats"])
     case["inputs"]["coors"] = bf16_round(case["inputs"]["coors"])      # a bf16 module is fed bf16 coordinates
+    if "edges" in case["inputs"]:
+        case["inputs"]["edges"] = bf16_round(case["inputs"]["edges"])
     mod = util.make_module(case, torch.bfloat16)
     out = util.run_module(mod, case, torch.bfloat16)
     torch.cuda.synchronize()
@@ -63,7 +80,7 @@ def test_fast_path_matches_oracle(name):
 
 
 def test_fast_path_falls_back_to_fp32_simt_when_unsupported():
-    case = cases.build_case(cases.SPECS["knn_edges_mask"])
+    case = cases.build_case(cases.SPECS["knn_mean_fourier"])      # fourier features: not on the tensor-core path
     mod = util.make_module(case, torch.bfloat16)
     out = util.run_module(mod, case, torch.bfloat16)
     assert mod.last_path == "fp32-simt" and out[0].dtype == torch.bfloat16
