@@ -61,14 +61,15 @@ inline Dims make_dims(const EgnnLayerDesc& d) {
 // ------------------------------------------------------------------ scalar math
 template <typename T> __device__ __forceinline__ T silu_acc(T x);
 template <> __device__ __forceinline__ float silu_acc<float>(float x) {
-  // x * sigmoid(x); __expf is ex2.approx based (2 ulp), the division is exact-rounded.
-  return x / (1.0f + __expf(-x));
+  // x * sigmoid(x): ex2.approx-based __expf (2 ulp) and rcp.approx-based __fdividef (2 ulp); for x < -88 the
+  // denominator overflows to +inf and the quotient is -0, which is the correct limit.
+  return __fdividef(x, 1.0f + __expf(-x));
 }
 template <> __device__ __forceinline__ double silu_acc<double>(double x) {
   return x / (1.0 + exp(-x));
 }
 template <typename T> __device__ __forceinline__ T sigmoid_acc(T x);
-template <> __device__ __forceinline__ float sigmoid_acc<float>(float x) { return 1.0f / (1.0f + __expf(-x)); }
+template <> __device__ __forceinline__ float sigmoid_acc<float>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 template <> __device__ __forceinline__ double sigmoid_acc<double>(double x) { return 1.0 / (1.0 + exp(-x)); }
 
 template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);

@@ -88,6 +88,24 @@ static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
   return EGNN_OK;
 }
 
+template <typename T, int MP, int PP>
+static int launch_pair_tiled(const PairArgs<T>& a, cudaStream_t st) {
+  const size_t smem = pair_tiled_smem_bytes<T>(a.s, a.L, PP);
+  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
+  static size_t smem_set[64] = {0};
+  int dev = 0;
+  EGNN_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 64 && smem_set[dev] < smem) {
+    EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_dense_tiled_kernel<T, MP, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set[dev] = smem;
+  }
+  dim3 grid(ceil_div(a.s.row1 - a.s.row0, 4 * PP), a.s.B);
+  pair_dense_tiled_kernel<T, MP, PP><<<grid, PAIR_THREADS, smem, st>>>(a);
+  EGNN_LAUNCH_CHECK();
+  count_launch();
+  return EGNN_OK;
+}
+
 template <typename T>
 static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* packed,
                         const EgnnLayerIO& io, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -147,8 +165,15 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
       else EGNN_TRY((launch_pair<T, 32, true>(a, st)));
     } else {
       a.TS = 32;
-      if (L.MP == 16) EGNN_TRY((launch_pair<T, 16, false>(a, st)));
-      else EGNN_TRY((launch_pair<T, 32, false>(a, st)));
+      constexpr int PP = 2;                                // rows per thread of the register-tiled dense kernel
+      int rc;
+      if (L.MP == 16) rc = launch_pair_tiled<T, 16, PP>(a, st);
+      else rc = launch_pair_tiled<T, 32, sizeof(T) == 4 ? 2 : 1>(a, st);
+      if (rc == EGNN_ERR_UNSUPPORTED) {                   // shared memory budget: thread-per-pair kernel
+        if (L.MP == 16) rc = launch_pair<T, 16, false>(a, st);
+        else rc = launch_pair<T, 32, false>(a, st);
+      }
+      EGNN_TRY(rc);
     }
   }
   // 4. node update  h' = node_mlp([LN(h) | m_i]) + h   (egnn_pytorch.py:335-337)

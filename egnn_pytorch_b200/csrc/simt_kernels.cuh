@@ -487,4 +487,262 @@ pair_kernel(const PairArgs<T> a) {
   }
 }
 
+// =====================================================================================
+// Dense all-pairs variant with register tiling over rows: a thread owns neighbour j and PP query rows, so every
+// W2 row fetched from shared memory feeds PP pairs (the thread-per-pair kernel above is bound by the 16
+// broadcast wavefronts per hidden channel that W2 costs; see profiles/).  One warp = PP rows x 32 neighbours,
+// 4 warps per CTA; per-row sums are reduced with shuffles per j-tile and kept in shared memory.
+// =====================================================================================
+template <typename T>
+inline size_t pair_tiled_smem_bytes(const Dims& s, const SimtPackLayout& L, int PP) {
+  size_t n = 0;
+  n += (size_t)PAIR_CH * L.MP;                         // W2s
+  n += (size_t)s.Q * PAIR_CH;                          // wqs
+  n += (size_t)PAIR_CH * 33;                           // Bs
+  if (s.Q > 1) n += (size_t)PP * s.Q * PAIR_THREADS;   // fs
+  n += (size_t)4 * s.m * L.MP + 8 * s.m + 2 * L.MP + 4;   // w3s, b3s, w4s, misc
+  n += (size_t)4 * PP * (L.MP + PAIR_CMAX + 4);        // per-row running sums
+  return round_up(n * sizeof(T), 16) + 16;
+}
+
+template <typename T, int MP, int PP>
+__global__ void __launch_bounds__(PAIR_THREADS)
+pair_dense_tiled_kernel(const PairArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims& s = a.s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int U = 4 * s.m;
+  const int qd = 2 * s.F;
+  constexpr int RS = MP + PAIR_CMAX + 4;          // row-sum record: m[MP] | csum[CMAX] | cnt | pad
+  const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS;
+  const bool upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
+
+  T* W2s = reinterpret_cast<T*>(smem_raw);
+  T* wqs = W2s + PAIR_CH * MP;
+  T* Bs = wqs + s.Q * PAIR_CH;
+  T* fs = Bs + PAIR_CH * 33;
+  T* w3s = fs + (s.Q > 1 ? PP * s.Q * PAIR_THREADS : 0);
+  T* b3s = w3s + U * MP;
+  T* w4s = b3s + U;
+  T* misc = w4s + U;
+  T* rows = misc + 2 * MP + 4;                    // [4 warps][PP][RS]
+
+  const T* pk = a.packed;
+  if (upd_coors) {
+    for (int x = tid; x < U * MP; x += PAIR_THREADS) w3s[x] = pk[a.L.w3 + x];
+    for (int x = tid; x < U; x += PAIR_THREADS) { b3s[x] = pk[a.L.b3 + x]; w4s[x] = pk[a.L.w4 + x]; }
+  }
+  for (int x = tid; x < 2 * MP + 4; x += PAIR_THREADS) misc[x] = pk[a.L.misc + x];
+  for (int x = tid; x < 4 * PP * RS; x += PAIR_THREADS) rows[x] = T(0);
+
+  int irow[PP];
+  bool rvalid[PP], mask_i[PP];
+  const T* Arow[PP];
+#pragma unroll
+  for (int p = 0; p < PP; ++p) {
+    const int ir = s.row0 + (blockIdx.x * 4 + warp) * PP + p;
+    rvalid[p] = ir < s.row1;
+    irow[p] = rvalid[p] ? ir : s.row0;
+    mask_i[p] = a.has_mask ? (a.mask[(size_t)b * s.N + irow[p]] != 0) : true;
+    Arow[p] = a.P + ((size_t)b * s.N + irow[p]) * a.ldP;
+  }
+  T* myrows = rows + (size_t)warp * PP * RS;
+
+  for (int s0 = 0; s0 < s.N; s0 += 32) {
+    const int jraw = s0 + lane;
+    const bool jv = jraw < s.N;
+    const int j = jv ? jraw : 0;
+    T xj[PAIR_CMAX];
+    {
+      const T* xjp = a.coors + ((size_t)b * s.N + j) * s.C;
+#pragma unroll
+      for (int c = 0; c < PAIR_CMAX; ++c) xj[c] = c < s.C ? xjp[c] : T(0);
+    }
+    T d[PP];
+    int lab[PP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      const T* xi = a.coors + ((size_t)b * s.N + irow[p]) * s.C;
+      T dd = T(0);
+#pragma unroll
+      for (int c = 0; c < PAIR_CMAX; ++c)
+        if (c < s.C) dd = sq_acc<T>(xi[c] - xj[c], dd);
+      d[p] = dd;
+      lab[p] = a.labels ? a.labels[((size_t)b * s.N + irow[p]) * s.N + j] : 0;
+      if (s.Q > 1) {
+        for (int q = 0; q < s.Q; ++q) {
+          T f;
+          if (q < s.F) f = sin(dd / T(1 << q));
+          else if (q < 2 * s.F) f = cos(dd / T(1 << (q - s.F)));
+          else if (q == qd) f = dd;
+          else f = a.edges[(((size_t)b * s.N + irow[p]) * s.N + j) * s.edge_dim + (q - s.Qd)];
+          fs[(p * s.Q + q) * PAIR_THREADS + tid] = f;
+        }
+      }
+    }
+
+    T acc[PP][MP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p)
+#pragma unroll
+      for (int o = 0; o < MP; ++o) acc[p][o] = T(0);
+
+    for (int c0 = 0; c0 < s.Hp; c0 += PAIR_CH) {
+      const int cn = min(PAIR_CH, s.Hp - c0);
+      __syncthreads();
+      for (int x = tid; x < cn * MP; x += PAIR_THREADS) W2s[x] = pk[a.L.w2t + (size_t)c0 * MP + x];
+      for (int x = tid; x < s.Q * cn; x += PAIR_THREADS) {
+        int q = x / cn, cc = x % cn;
+        wqs[q * PAIR_CH + cc] = pk[a.L.wq + (size_t)q * s.Hp + c0 + cc];
+      }
+      {
+        const int cc = tid % PAIR_CH, jj0 = tid / PAIR_CH;
+        for (int jj = jj0; jj < 32; jj += PAIR_THREADS / PAIR_CH) {
+          T v = T(0);
+          if (cc < cn && s0 + jj < s.N) v = a.P[((size_t)b * s.N + s0 + jj) * a.ldP + s.Hp + c0 + cc];
+          Bs[cc * 33 + jj] = v;
+        }
+      }
+      __syncthreads();
+
+      for (int cc = 0; cc < cn; cc += 4) {
+        Vec4<T> wd;
+        wd.load(wqs + qd * PAIR_CH + cc);
+        T bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) bv[u] = Bs[(cc + u) * 33 + lane];
+        T pre[PP][4];
+#pragma unroll
+        for (int p = 0; p < PP; ++p) {
+          Vec4<T> av;
+          av.load_g(Arow[p] + c0 + cc);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pre[p][u] = fma_t(wd.v[u], d[p], av.v[u] + bv[u]);
+          if (a.labels) {
+            Vec4<T> tv;
+            tv.load_g(pk + a.L.tab + (size_t)lab[p] * s.Hp + c0 + cc);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pre[p][u] += tv.v[u];
+          }
+        }
+        if (s.Q > 1) {
+          for (int q = 0; q < s.Q; ++q) {
+            if (q == qd) continue;
+            Vec4<T> wv;
+            wv.load(wqs + q * PAIR_CH + cc);
+#pragma unroll
+            for (int p = 0; p < PP; ++p) {
+              const T f = fs[(p * s.Q + q) * PAIR_THREADS + tid];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) pre[p][u] = fma_t(wv.v[u], f, pre[p][u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T* w2 = W2s + (cc + u) * MP;
+          T hdn[PP];
+#pragma unroll
+          for (int p = 0; p < PP; ++p) hdn[p] = silu_acc<T>(pre[p][u]);
+#pragma unroll
+          for (int v4 = 0; v4 < MP; v4 += 4) {
+            Vec4<T> wv;
+            wv.load(w2 + v4);
+#pragma unroll
+            for (int p = 0; p < PP; ++p)
+#pragma unroll
+              for (int z = 0; z < 4; ++z) acc[p][v4 + z] = fma_t(hdn[p], wv.v[z], acc[p][v4 + z]);
+          }
+        }
+      }
+    }
+
+    // ---- epilogue of this j-tile for the PP rows
+    const bool mask_j = a.has_mask ? (a.mask[(size_t)b * s.N + j] != 0) : true;
+#pragma unroll
+    for (int p = 0; p < PP; ++p) {
+      T mm[MP];
+#pragma unroll
+      for (int o = 0; o < MP; ++o) mm[o] = silu_acc<T>(acc[p][o] + misc[o]);
+      if (a.flags & EGNN_FLAG_SOFT_EDGES) {
+        T z = misc[2 * MP + 0];
+#pragma unroll
+        for (int o = 0; o < MP; ++o) z = fma_t(misc[MP + o], mm[o], z);
+        const T gate = sigmoid_acc<T>(z);
+#pragma unroll
+        for (int o = 0; o < MP; ++o) mm[o] *= gate;
+      }
+      const bool pair_valid = rvalid[p] && jv;
+      const bool pm = pair_valid && (a.has_mask ? (mask_i[p] && mask_j) : true);
+      T rec[RS];
+#pragma unroll
+      for (int x = 0; x < RS; ++x) rec[x] = T(0);
+      if (upd_coors) {
+        T w = misc[2 * MP + 1];
+        for (int u = 0; u < U; ++u) {
+          T t = b3s[u];
+          const T* w3 = w3s + u * MP;
+#pragma unroll
+          for (int o = 0; o < MP; o += 4) {
+            Vec4<T> wv;
+            wv.load(w3 + o);
+#pragma unroll
+            for (int z = 0; z < 4; ++z) t = fma_t(wv.v[z], mm[o + z], t);
+          }
+          w = fma_t(w4s[u], silu_acc<T>(t), w);
+        }
+        if (!pm) w = T(0);
+        if (a.flags & EGNN_FLAG_CLAMP) w = w < -a.clamp ? -a.clamp : (w > a.clamp ? a.clamp : w);
+        if (!pair_valid) w = T(0);
+        if (a.flags & EGNN_FLAG_NORM_COORS) {
+          const T nrm = sqrt(d[p]);
+          w *= misc[2 * MP + 2] / (nrm > T(1e-8) ? nrm : T(1e-8));
+        }
+        const T* xi = a.coors + ((size_t)b * s.N + irow[p]) * s.C;
+#pragma unroll
+        for (int c = 0; c < PAIR_CMAX; ++c)
+          if (c < s.C) rec[MP + c] = w * (xi[c] - xj[c]);
+      }
+      if (upd_feats && pm) {
+#pragma unroll
+        for (int o = 0; o < MP; ++o) rec[o] = mm[o];
+        rec[MP + PAIR_CMAX] = T(1);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int x = 0; x < MP + PAIR_CMAX + 1; ++x) rec[x] += shfl_xor_t<T>(rec[x], off);
+      if (lane == 0) {
+#pragma unroll
+        for (int x = 0; x < MP + PAIR_CMAX + 1; ++x) myrows[p * RS + x] += rec[x];
+      }
+    }
+  }
+
+  __syncwarp();
+  if (lane < PP && rvalid[0]) {
+    // lane p writes row p (rvalid is monotone in p)
+    int p = lane;
+    const int ir = s.row0 + (blockIdx.x * 4 + warp) * PP + p;
+    if (ir < s.row1) {
+      const size_t node = (size_t)b * s.N + ir;
+      const T* rec = myrows + p * RS;
+      if (upd_feats) {
+        T inv = T(1);
+        if (a.flags & EGNN_FLAG_POOL_MEAN) {
+          const T cnt = rec[MP + PAIR_CMAX];
+          if (a.has_mask) inv = cnt > T(0) ? T(1) / cnt : T(0);
+          else inv = T(1) / T(s.N);
+        }
+        for (int o = 0; o < s.m; ++o) a.m_out[node * a.ld_m + o] = rec[o] * inv;
+      }
+      if (upd_coors) {
+        const T* xi = a.coors + node * s.C;
+        for (int c = 0; c < s.C; ++c) a.coors_out[node * s.C + c] = rec[MP + c] + xi[c];
+      }
+    }
+  }
+}
+
 }  // namespace egnn

@@ -83,12 +83,14 @@ for dt in (torch.bfloat16, torch.float32):
 o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.float32)
 f, x, m = torch.randint(0, 21, (1, 1024), generator=g).to(dev), torch.randn(1, 1024, 3, generator=g).to(dev), torch.ones(1, 1024, dtype=torch.bool, device=dev)
 run("c3 Network depth3 dim32 N=1024 k=8 fp32", o, t, (f, x), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
+o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.bfloat16)
+run("c3 Network depth3 dim32 N=1024 k=8 bf16", o, t, (f, x.bfloat16()), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
 # c4 (8 graphs = one GPU's share of B=64)
-for dt in (torch.float32,):
+for dt in (torch.bfloat16, torch.float32):
     o, t = build(EGNN, R, dict(dim=256, edge_dim=4, num_nearest_neighbors=32), dt)
     f, x = torch.randn(8, 4096, 256, generator=g).to(dev, dt), torch.randn(8, 4096, 3, generator=g).to(dev, dt)
     e = torch.randn(8, 4096, 4096, 4, generator=g).to(dev, dt)
-    run(f"c4 EGNN(256,e4) k=32 N=4096 B=8/GPU {str(dt)[6:]}", o, t, (f, x, e), {}, 8 * 4096 * 4096, 8 * 4096 * 32, 5, 2)
+    run(f"c4 EGNN(256,e4) k=32 N=4096 B=8/GPU {str(dt)[6:]}", o, t, (f, x, e), {}, 8 * 4096 * 4096, 8 * 4096 * 32, 10, 2)
     del e
 # c5
 o, t = build(EGNN_Network, RN, dict(num_tokens=21, dim=32, depth=3, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True), torch.float32)
