@@ -73,6 +73,21 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswizzle(uint32_t saddr, u
   return d;                        // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
 
+// K-major operand in the 128-byte-swizzle canonical layout: rows of 128 B (64 bf16), groups of 8 rows = 1024 B
+// (`sbo`), the 16-byte chunk index of a row XOR-ed with (row % 8).  Tile base 1024-byte aligned; a K=16 step
+// advances the start address by 32 B inside the swizzle atom.  (Measured on B200: the no-swizzle layout above is
+// read by the tensor core at ~16 B/clk, this one at full rate -- it matters for M=N=128 GEMM tiles, not for the
+// 512-byte W2 slabs of the fused edge kernels.)
+__device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                      // LBO: unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;            // SBO: 8-row group stride
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // layout_type = SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B, fp32 D, both operands K-major
 // (cute::UMMA::InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {

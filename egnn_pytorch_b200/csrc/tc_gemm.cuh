@@ -3,8 +3,8 @@
 // used for  A' = 0.5 (h W1_i^T + b1)  (fp32 out),  B' = 0.5 h W1_j^T  (bf16 out)   [split of egnn_pytorch.py:287]
 //           h1 = SiLU([LN(h) | m_i] Wn1^T + bn1),  h' = h1 Wn2^T + bn2 + h                   [egnn_pytorch.py:335-337]
 //
-// 128x128 output tile per CTA, BK = 64, two shared-memory stages filled with cp.async straight into the
-// UMMA no-swizzle K-major core-matrix layout (8 rows x 16 B per core matrix), one elected thread issues
+// 128x128 output tile per CTA, BK = 64, a six-stage shared-memory ring filled with cp.async straight into the
+// UMMA swizzle-128B K-major layout (128-byte rows, 8-row groups), one elected thread issues
 // tcgen05.mma (M=128, N=128, K=16) x4 per stage, completion tracked with tcgen05.commit -> mbarrier,
 // epilogue reads the accumulator with tcgen05.ld (thread == row).
 #pragma once
@@ -25,18 +25,24 @@ struct TcGemmArgs {
 };
 
 constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 64;
-constexpr int GEMM_TILE_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB per operand per stage
-constexpr int GEMM_SMEM_BYTES = 2 * 2 * GEMM_TILE_BYTES + 1024;   // 2 stages x (A, W) + alignment slack
+constexpr int GEMM_TILE_BYTES = GEMM_BM * GEMM_BK * 2;            // 16 KB per operand per stage (128 rows x 128 B)
+constexpr int GEMM_STAGES = 3;   // shared-memory ring (3 x 32 KB: two CTAs per SM, one tile's epilogue overlaps the other's main loop)
+constexpr int GEMM_DIST = 2;     // copies run 2 k-steps ahead of the MMAs
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * GEMM_TILE_BYTES + 1024;
 
 __global__ void __launch_bounds__(128, 1) tc_gemm_kernel(const TcGemmArgs g) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t mma_done[2];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint64_t full[GEMM_STAGES], mma_done[GEMM_STAGES];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * GEMM_BN;
-  const uint32_t s_base = tc::smem_u32(smem);
+  const uint32_t s_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle-128B tiles need 1024-byte alignment
+  unsigned char* smem = smem_raw + (s_base - tc::smem_u32(smem_raw));
 
-  if (tid == 0) { tc::mbar_init(&mma_done[0], 1); tc::mbar_init(&mma_done[1], 1); tc::mbar_fence_init(); }
+  if (tid == 0) {
+    for (int x = 0; x < GEMM_STAGES; ++x) { tc::mbar_init(&full[x], 128); tc::mbar_init(&mma_done[x], 1); }
+    tc::mbar_fence_init();
+  }
   if (warp == 0) tc::tmem_alloc<128>(&tmem_base_s);
   tc::tc_fence_before();
   __syncthreads();
@@ -44,98 +50,98 @@ __global__ void __launch_bounds__(128, 1) tc_gemm_kernel(const TcGemmArgs g) {
   const uint32_t tmem = tmem_base_s;
 
   const int nk = (g.K + GEMM_BK - 1) / GEMM_BK;
+  // Copy mapping: 8 consecutive lanes fetch the 8 16-byte K-chunks of one row (one fully used 128-byte line per
+  // row) and drop them into the row's 128 bytes of the swizzle-128B layout (chunk kc -> position kc ^ (row % 8)):
+  // coalesced on the global side, conflict-free on the shared side.
   auto load_stage = [&](int kt) {
-    const int st = kt & 1;
+    const int st = kt % GEMM_STAGES;
     const uint32_t sA = s_base + st * 2 * GEMM_TILE_BYTES, sW = sA + GEMM_TILE_BYTES;
-    const int rowA = m0 + tid, rowW = n0 + tid;
+    const int kc = tid & 7, k = kt * GEMM_BK + kc * 8;
+    const bool kin = k < g.K;
 #pragma unroll
-    for (int kc = 0; kc < 8; ++kc) {
-      const int k = kt * GEMM_BK + kc * 8;
-      const bool kin = k < g.K;
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 16 + (tid >> 3);
+      const int rowA = m0 + r, rowW = n0 + r;
       const bool va = kin && rowA < g.M, vw = kin && rowW < g.Nv;
       const __nv_bfloat16* pa = va ? g.A + (size_t)rowA * g.lda + k : g.A;
       const __nv_bfloat16* pw = vw ? g.W + (size_t)rowW * g.ldw + k : g.W;
-      tc::cp_async16(sA + kc * 2048 + tid * 16, pa, va ? 16u : 0u);
-      tc::cp_async16(sW + kc * 2048 + tid * 16, pw, vw ? 16u : 0u);
+      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((kc ^ (r & 7)) << 4);
+      tc::cp_async16(sA + off, pa, va ? 16u : 0u);
+      tc::cp_async16(sW + off, pw, vw ? 16u : 0u);
     }
-    tc::cp_async_commit();
   };
 
+  // Multi-stage ring.  Every thread copies its rows of stage kt+DIST, waits for its own copies of stage kt
+  // (cp.async.wait_group), makes them visible to the tensor core (fence.proxy.async) and arrives on full[kt];
+  // thread 0 then issues the stage's MMAs.  A slot is re-filled only after tcgen05.commit signalled mma_done.
   constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 128);
-  load_stage(0);
+  for (int kt = 0; kt < GEMM_DIST; ++kt) {
+    if (kt < nk) load_stage(kt);
+    tc::cp_async_commit();
+  }
   for (int kt = 0; kt < nk; ++kt) {
-    if (kt + 1 < nk) {
-      // stage (kt+1)&1 was last read by the MMAs of iteration kt-1
-      if (kt >= 1) tc::mbar_wait(&mma_done[(kt + 1) & 1], ((kt - 1) >> 1) & 1);
-      load_stage(kt + 1);
-      tc::cp_async_wait<1>();
-    } else {
-      tc::cp_async_wait<0>();
+    const int nxt = kt + GEMM_DIST;
+    if (nxt < nk) {
+      const int prev = nxt - GEMM_STAGES;            // iteration whose MMAs last read slot nxt % STAGES
+      if (prev >= 0) tc::mbar_wait(&mma_done[nxt % GEMM_STAGES], (prev / GEMM_STAGES) & 1);
+      load_stage(nxt);
     }
+    tc::cp_async_commit();
+    tc::cp_async_wait<GEMM_DIST>();        // this thread's copies of stage kt have landed
     tc::fence_proxy_async_smem();          // cp.async (generic proxy) -> tensor core (async proxy)
-    __syncthreads();
+    tc::mbar_arrive(&full[kt % GEMM_STAGES]);
     if (tid == 0) {
+      tc::mbar_wait(&full[kt % GEMM_STAGES], (kt / GEMM_STAGES) & 1);
       tc::tc_fence_after();
-      const uint32_t sA = s_base + (kt & 1) * 2 * GEMM_TILE_BYTES, sW = sA + GEMM_TILE_BYTES;
+      const uint32_t sA = s_base + (kt % GEMM_STAGES) * 2 * GEMM_TILE_BYTES, sW = sA + GEMM_TILE_BYTES;
 #pragma unroll
       for (int kk = 0; kk < GEMM_BK / 16; ++kk) {
-        constexpr uint32_t lbo = 2048u, sbo = 128u;   // K-adjacent / M-adjacent core matrices of the tile
-        const uint64_t da = tc::smem_desc_kmajor_noswizzle(sA + kk * 4096, lbo, sbo);
-        const uint64_t dw = tc::smem_desc_kmajor_noswizzle(sW + kk * 4096, lbo, sbo);
+        const uint64_t da = tc::smem_desc_kmajor_sw128(sA + kk * 32);   // K=16 step = 32 B inside the swizzle atom
+        const uint64_t dw = tc::smem_desc_kmajor_sw128(sW + kk * 32);
         tc::mma_ss(tmem, da, dw, IDESC, (kt > 0 || kk > 0) ? 1u : 0u);
       }
-      tc::mma_commit(&mma_done[kt & 1]);
+      tc::mma_commit(&mma_done[kt % GEMM_STAGES]);
     }
   }
   // the last commit covers every MMA issued before it
-  tc::mbar_wait(&mma_done[(nk - 1) & 1], ((nk - 1) >> 1) & 1);
+  tc::mbar_wait(&mma_done[(nk - 1) % GEMM_STAGES], ((nk - 1) / GEMM_STAGES) & 1);
   tc::tc_fence_after();
 
-  const int row = m0 + warp * 32 + lane;
+  // Epilogue.  tcgen05.ld hands every thread one ROW of the accumulator; storing rows from lanes would touch 32
+  // different lines per instruction, so each warp transposes its 32x32 block through shared memory (the pipeline
+  // buffers are free now) and writes with lane = column: 128-byte (fp32) / 64-byte (bf16) contiguous stores,
+  // bias and residual loaded once per column / coalesced.
+  float* stg = reinterpret_cast<float*>(smem) + warp * (32 * 33);
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
   for (int cb = 0; cb < GEMM_BN / 32; ++cb) {
+    const int col0 = n0 + cb * 32;
+    if (col0 >= g.Nout) break;
     uint32_t r[32];
     tc::tmem_ld32(trow + cb * 32, r);
     tc::tmem_wait_ld();
-    const int col0 = n0 + cb * 32;
-    if (row < g.M && col0 < g.Nout) {
-      float v[32];
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int col = col0 + q;
-        float x = 0.f;
-        if (col < g.Nv) {
-          x = __uint_as_float(r[q]);
-          if (g.bias) x += g.bias[col];
-          x *= g.scale;
-          if (g.act == 1) x = x / (1.0f + __expf(-x));
-          if (g.R) x += __bfloat162float(g.R[(size_t)row * g.ldr + col]);
-        }
-        v[q] = x;
+    for (int q = 0; q < 32; ++q) stg[lane * 33 + q] = __uint_as_float(r[q]);
+    __syncwarp();
+    const int col = col0 + lane;
+    const bool cin = col < g.Nout, cv = col < g.Nv;
+    const float bcol = (cv && g.bias) ? g.bias[col] : 0.f;
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      const int row = m0 + warp * 32 + rr;
+      if (row >= g.M) break;
+      float x = 0.f;
+      if (cv) {
+        x = (stg[rr * 33 + lane] + bcol) * g.scale;
+        if (g.act == 1) x = __fdividef(x, 1.0f + __expf(-x));
+        if (g.R) x += __bfloat162float(g.R[(size_t)row * g.ldr + col]);
       }
-      if (g.out_f32) {
-        float* o = static_cast<float*>(g.out) + (size_t)row * g.ldo + col0;
-#pragma unroll
-        for (int q = 0; q < 32; q += 4) {
-          if (col0 + q + 4 <= g.Nout) *reinterpret_cast<float4*>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-          else for (int z = 0; z < 4; ++z) if (col0 + q + z < g.Nout) o[q + z] = v[q + z];
-        }
-      } else {
-        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(g.out) + (size_t)row * g.ldo + col0;
-#pragma unroll
-        for (int q = 0; q < 32; q += 8) {
-          if (col0 + q + 8 <= g.Nout) {
-            uint4 pk;
-            pk.x = tc::pack_bf16x2(v[q], v[q + 1]); pk.y = tc::pack_bf16x2(v[q + 2], v[q + 3]);
-            pk.z = tc::pack_bf16x2(v[q + 4], v[q + 5]); pk.w = tc::pack_bf16x2(v[q + 6], v[q + 7]);
-            *reinterpret_cast<uint4*>(o + q) = pk;
-          } else {
-            for (int z = 0; z < 8; ++z) if (col0 + q + z < g.Nout) o[q + z] = __float2bfloat16(v[q + z]);
-          }
-        }
+      if (cin) {
+        if (g.out_f32) static_cast<float*>(g.out)[(size_t)row * g.ldo + col] = x;
+        else static_cast<__nv_bfloat16*>(g.out)[(size_t)row * g.ldo + col] = __float2bfloat16(x);
       }
     }
+    __syncwarp();
   }
   tc::tc_fence_before();
   __syncthreads();
