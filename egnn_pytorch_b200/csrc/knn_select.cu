@@ -81,63 +81,102 @@ __device__ __forceinline__ void warp_merge(T& bkey, int& bidx, T ckey, int cidx,
   for (int stride = 16; stride > 0; stride >>= 1) cmpex<T>(bkey, bidx, lane, stride, true);
 }
 
-constexpr int SEL_WARPS = 4;
+constexpr int SEL_WARPS = 8;        // rows per CTA (one warp each), all of the same graph
+constexpr int SEL_JC = 1024;        // candidates staged per pass: coordinates as SoA + mask bytes in shared memory
+
+template <typename T>
+inline size_t sel_smem_bytes(int C) {
+  return (size_t)C * SEL_JC * sizeof(T) + SEL_JC + (size_t)SEL_WARPS * 64 * (sizeof(T) + sizeof(int)) + 64;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 knn_warp_select_kernel(const SelArgs<T> a) {
-  __shared__ T qkey[SEL_WARPS][64];
-  __shared__ int qidx[SEL_WARPS][64];
+  extern __shared__ __align__(16) unsigned char sel_sm[];
+  T* xs = reinterpret_cast<T*>(sel_sm);                                   // [C][JC]
+  T* qkey = xs + (size_t)a.C * SEL_JC;                                    // [WARPS][64]
+  int* qidx = reinterpret_cast<int*>(qkey + SEL_WARPS * 64);              // [WARPS][64]
+  uint8_t* ms = reinterpret_cast<uint8_t*>(qidx + SEL_WARPS * 64);        // [JC]
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int row = blockIdx.x * SEL_WARPS + warp;     // b*N + i
-  if (row >= a.B * a.N) return;
-  const int b = row / a.N, i = row % a.N;
-  const T* xi = a.coors + (size_t)row * a.C;
+  const int b = blockIdx.y;
+  const int iraw = blockIdx.x * SEL_WARPS + warp;
+  const bool rv = iraw < a.N;
+  const int i = rv ? iraw : a.N - 1;
+  const size_t row = (size_t)b * a.N + i;
+  T xi[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) xi[c] = c < a.C ? a.coors[row * a.C + c] : T(0);
   const bool mask_i = a.mask ? a.mask[row] != 0 : true;
+  const uint8_t* adjrow = a.adj ? a.adj + ((size_t)(a.adj_batched ? b : 0) * a.N + i) * a.N : nullptr;
   const T INF = T(INFINITY);
   const int IMAX = 0x7fffffff;
+  T* myqk = qkey + warp * 64;
+  int* myqi = qidx + warp * 64;
 
   T bkey = INF; int bidx = IMAX;       // lane l: l-th smallest so far
   T thr_key = INF; int thr_idx = IMAX; // the k-th smallest so far
   int count = 0;                       // queued candidates (warp-uniform)
 
-  for (int j0 = 0; j0 < a.N; j0 += 32) {
-    const int j = j0 + lane;
-    T key = INF;
-    if (j < a.N) key = rank_of<T>(a, b, i, j, xi, mask_i);
-    const bool pass = j < a.N && lex_less<T>(key, j, thr_key, thr_idx);
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (bal == 0) continue;
-    if (pass) {
-      const int pos = count + __popc(bal & ((1u << lane) - 1));
-      qkey[warp][pos] = key;
-      qidx[warp][pos] = j;
+  for (int jc0 = 0; jc0 < a.N; jc0 += SEL_JC) {
+    const int jn = min(SEL_JC, a.N - jc0);
+    __syncthreads();                   // previous pass fully consumed
+    for (int e = threadIdx.x; e < jn * a.C; e += SEL_WARPS * 32) {
+      const int jj = e / a.C, c = e - jj * a.C;
+      xs[c * SEL_JC + jj] = a.coors[((size_t)b * a.N + jc0) * a.C + e];
     }
-    count += __popc(bal);
-    __syncwarp();
-    if (count >= 32) {
-      T ckey = qkey[warp][lane];
-      int cidx = qidx[warp][lane];
-      __syncwarp();
-      // shift the tail of the queue down
-      if (lane + 32 < count) {
-        T tk = qkey[warp][lane + 32]; int ti = qidx[warp][lane + 32];
-        qkey[warp][lane] = tk; qidx[warp][lane] = ti;
+    if (a.mask)
+      for (int jj = threadIdx.x; jj < jn; jj += SEL_WARPS * 32) ms[jj] = a.mask[(size_t)b * a.N + jc0 + jj];
+    __syncthreads();
+
+    for (int j0 = 0; j0 < jn; j0 += 32) {
+      const int jj = j0 + lane, j = jc0 + jj;
+      const bool jvalid = jj < jn;
+      T key = INF;
+      if (jvalid) {
+        T d = T(0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c < a.C) d = sq_acc<T>(xi[c] - xs[c * SEL_JC + jj], d);
+        if (a.mask && !(mask_i && ms[jj])) d = T(1e5);
+        if (adjrow) {
+          if (i == j) d = T(-1);
+          else if (adjrow[j]) d = T(0);
+        }
+        key = d;
       }
-      count -= 32;
+      const bool pass = jvalid && lex_less<T>(key, j, thr_key, thr_idx);
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (bal == 0) continue;
+      if (pass) {
+        const int pos = count + __popc(bal & ((1u << lane) - 1));
+        myqk[pos] = key;
+        myqi[pos] = j;
+      }
+      count += __popc(bal);
       __syncwarp();
-      warp_merge<T>(bkey, bidx, ckey, cidx, lane);
-      thr_key = shfl_idx_t<T>(bkey, a.k - 1);
-      thr_idx = __shfl_sync(0xffffffffu, bidx, a.k - 1);
+      if (count >= 32) {
+        T ckey = myqk[lane];
+        int cidx = myqi[lane];
+        __syncwarp();
+        if (lane + 32 < count) {         // shift the tail of the queue down
+          T tk = myqk[lane + 32]; int ti = myqi[lane + 32];
+          myqk[lane] = tk; myqi[lane] = ti;
+        }
+        count -= 32;
+        __syncwarp();
+        warp_merge<T>(bkey, bidx, ckey, cidx, lane);
+        thr_key = shfl_idx_t<T>(bkey, a.k - 1);
+        thr_idx = __shfl_sync(0xffffffffu, bidx, a.k - 1);
+      }
     }
   }
   if (count > 0) {
-    T ckey = lane < count ? qkey[warp][lane] : INF;
-    int cidx = lane < count ? qidx[warp][lane] : IMAX;
+    T ckey = lane < count ? myqk[lane] : INF;
+    int cidx = lane < count ? myqi[lane] : IMAX;
     warp_merge<T>(bkey, bidx, ckey, cidx, lane);
   }
-  if (lane < a.k) {
-    const size_t o = (size_t)row * a.k + lane;
+  if (rv && lane < a.k) {
+    const size_t o = row * a.k + lane;
     a.out_idx[o] = bidx;
     if (a.out_ok) a.out_ok[o] = bkey <= a.valid_radius ? 1 : 0;
   }
@@ -192,7 +231,17 @@ static int launch_select(int B, int N, int C, int k, const void* coors, const ui
   a.out_idx = out_idx; a.out_ok = out_ok;
   const int rows = B * N;
   if (k <= 32) {
-    knn_warp_select_kernel<T><<<ceil_div(rows, SEL_WARPS), SEL_WARPS * 32, 0, st>>>(a);
+    const size_t smem = sel_smem_bytes<T>(C);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    EGNN_CUDA_TRY(cudaGetDevice(&dev));
+    if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sel_smem_bytes<T>(8)));
+      attr_set[dev] = true;
+    }
+    dim3 grid(ceil_div(N, SEL_WARPS), B);
+    knn_warp_select_kernel<T><<<grid, SEL_WARPS * 32, smem, st>>>(a);
   } else {
     int Npad = 1;
     while (Npad < N) Npad <<= 1;
@@ -209,7 +258,7 @@ int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* c
                         const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
                         uint8_t* out_ok, cudaStream_t st) {
   if (!coors || !out_idx) return EGNN_ERR_NULL;
-  if (B <= 0 || N <= 0 || C <= 0 || C > 8 || k <= 0 || k > N) return EGNN_ERR_SHAPE;
+  if (B <= 0 || B > 65535 || N <= 0 || C <= 0 || C > 8 || k <= 0 || k > N) return EGNN_ERR_SHAPE;
   if (dtype == EGNN_DTYPE_F64)
     return launch_select<double>(B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx, out_ok, st);
   return launch_select<float>(B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx, out_ok, st);

@@ -69,6 +69,28 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _as_u8(t, dev):
+    """bool / uint8 / numeric 0-1 tensor -> contiguous uint8 on `dev`, zero-copy when it already is one."""
+    if t is None:
+        return None
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.dtype == torch.bool:
+        t = t.view(torch.uint8)
+    elif t.dtype != torch.uint8:
+        t = t.ne(0).view(torch.uint8)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _as(t, dev, dtype):
+    """Tensor on `dev` in `dtype`, contiguous; no work when it already is."""
+    if t is None:
+        return None
+    if t.device == dev and t.dtype == dtype and t.is_contiguous():
+        return t.detach()
+    return t.detach().to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
+
 # ----------------------------------------------------------------------------- small modules
 
 
@@ -125,6 +147,8 @@ class EGNN(nn.Module):
         self.precision = precision
         self.last_path = None          # 'fp64-simt' | 'fp32-simt' | 'bf16-tcgen05' of the last call
         self._stage = {}
+        self._tc_unsupported = set()
+        self._call_cache = {}
         self.apply(self._init)
 
     def _init(self, module):
@@ -202,7 +226,7 @@ class EGNN(nn.Module):
         if use_nearest:
             k = self.num_nearest_neighbors
             if exists(adj_mat):
-                adj_u8 = adj_mat.to(device=dev).ne(0).to(torch.uint8).contiguous()
+                adj_u8 = _as_u8(adj_mat, dev)
                 if adj_u8.dim() == 3:
                     flags |= nat.FLAG_ADJ_BATCHED
                 if self.only_sparse_neighbors:
@@ -212,14 +236,19 @@ class EGNN(nn.Module):
             if not (0 < k <= n):
                 raise RuntimeError(f"number of neighbours k={k} must satisfy 0 < k <= N={n} (torch.topk would raise)")
 
-        for attempt_dt in ([kdt, torch.float32] if kdt == torch.bfloat16 else [kdt]):
-            try:
-                return self._run(lib, dev, attempt_dt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
-                                 b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
-            except nat.EgnnNativeError as e:
-                if e.code == nat.ERR_UNSUPPORTED and attempt_dt == torch.bfloat16:
-                    continue        # tensor-core kernels do not cover this option set: fp32 SIMT kernels
+        cfg_key = (c, k > 0, min(k, 33), cont_edge_dim, label_dim, _rows is None)
+        if kdt == torch.bfloat16 and cfg_key in self._tc_unsupported:
+            kdt = torch.float32
+        try:
+            return self._run(lib, dev, kdt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
+                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
+        except nat.EgnnNativeError as e:
+            if e.code != nat.ERR_UNSUPPORTED or kdt != torch.bfloat16:
                 raise
+        # the tensor-core kernels do not cover this option set: fp32 SIMT kernels (still on the GPU); remembered
+        self._tc_unsupported.add(cfg_key)
+        return self._run(lib, dev, torch.float32, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
+                         b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
 
     def _run(self, lib, dev, kdt, feats, coors, edges, mask, adj_u8, labels, label_emb, b, n, c, k, flags,
              cont_edge_dim, label_dim, rows):
@@ -236,12 +265,22 @@ class EGNN(nn.Module):
                 st["packed"] = {}
             T["label_emb"] = lab_w
 
-        desc = nat.LayerDesc(
-            abi_version=nat.ABI_VERSION, dtype=_KERNEL_DTYPE[kdt], B=b, N=n, C=c, dim=self.dim,
-            edge_dim=cont_edge_dim, label_dim=label_dim, num_labels=0 if label_emb is None else label_emb.shape[0],
-            m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
-            valid_radius=float(self.valid_radius), clamp=float(self.coor_weights_clamp_value or 0.0),
-            row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0)
+        ckey = (kdt, b, n, c, k, flags, cont_edge_dim, label_dim, 0 if label_emb is None else label_emb.shape[0], rows)
+        cc = self._call_cache.get(ckey)
+        if cc is None:
+            desc = nat.LayerDesc(
+                abi_version=nat.ABI_VERSION, dtype=_KERNEL_DTYPE[kdt], B=b, N=n, C=c, dim=self.dim,
+                edge_dim=cont_edge_dim, label_dim=label_dim, num_labels=0 if label_emb is None else label_emb.shape[0],
+                m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
+                valid_radius=float(self.valid_radius), clamp=float(self.coor_weights_clamp_value or 0.0),
+                row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0)
+            nb = C.c_size_t()
+            nat.check("egnn_layer_workspace_bytes", lib.egnn_layer_workspace_bytes(C.byref(desc), C.byref(nb)))
+            cc = (desc, nb.value)
+            if len(self._call_cache) > 64:
+                self._call_cache.clear()
+            self._call_cache[ckey] = cc
+        desc, ws_bytes = cc
         wkey = None if lab_w is None else (label_emb.data_ptr(), label_emb._version)
         w = st["wstruct"].get(wkey)
         if w is None:
@@ -263,11 +302,8 @@ class EGNN(nn.Module):
                           lib.egnn_layer_pack_weights(C.byref(desc), C.byref(w), _ptr(packed), nb.value, stream))
                 st["packed"] = {pkey: packed}
 
-            f_in = feats.detach().to(device=dev, dtype=kdt, non_blocking=True).contiguous()
-            x_in = coors.detach().to(device=dev, dtype=cdt, non_blocking=True).contiguous()
-            e_in = None if edges is None else edges.detach().to(device=dev, dtype=kdt, non_blocking=True).contiguous()
-            m_in = None if mask is None else mask.to(device=dev, non_blocking=True).ne(0).to(torch.uint8).contiguous()
-            l_in = None if labels is None else labels.to(device=dev, dtype=torch.uint8).contiguous()
+            f_in, x_in, e_in = _as(feats, dev, kdt), _as(coors, dev, cdt), _as(edges, dev, kdt)
+            m_in, l_in = _as_u8(mask, dev), _as_u8(labels, dev)
             f_out = torch.empty_like(f_in)
             x_out = torch.empty_like(x_in)
             if rows is not None:       # rows outside the range keep the input values
@@ -278,9 +314,7 @@ class EGNN(nn.Module):
                              mask=None if m_in is None else m_in.data_ptr(),
                              adj=None if adj_u8 is None else adj_u8.data_ptr(),
                              feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr())
-            nb = C.c_size_t()
-            nat.check("egnn_layer_workspace_bytes", lib.egnn_layer_workspace_bytes(C.byref(desc), C.byref(nb)))
-            ws = _workspace(dev, nb.value)
+            ws = _workspace(dev, ws_bytes)
             nat.check("egnn_layer_forward",
                       lib.egnn_layer_forward(C.byref(desc), C.byref(w), _ptr(packed), C.byref(io), _ptr(ws),
                                              ws.numel(), stream))
