@@ -4,6 +4,7 @@
 #include "simt_kernels.cuh"
 #include "fast_path.h"
 #include "profile.h"
+#include <algorithm>
 
 namespace egnn {
 
@@ -36,8 +37,15 @@ static inline size_t elem_size(int dtype) { return dtype == EGNN_DTYPE_F64 ? 8 :
 
 // ------------------------------------------------------------------ SIMT workspace
 struct SimtWs {
-  size_t P, node_in, h1, nbr_idx, nbr_ok, total;
+  size_t P, node_in, h1, nbr_idx, nbr_ok, hpart, total;
+  int hsplit;
 };
+// Tiny dense graphs (the README example, BASELINE config 1): too few (row, neighbour) tiles to fill the GPU, so the
+// hidden axis is split over CTAs and the partial sums take one trip through the workspace.
+static int simt_hsplit(const Dims& s) {
+  if (s.k != 0 || (long long)s.B * s.N * s.N > 4096 || s.Hp < 512 || s.row0 != 0 || s.row1 != s.N) return 1;
+  return std::min(32, ceil_div(s.Hp, PAIR_CH));
+}
 static SimtWs simt_ws_layout(const Dims& s, size_t es, uint32_t flags) {
   SimtWs w;
   size_t o = 0;
@@ -48,6 +56,8 @@ static SimtWs simt_ws_layout(const Dims& s, size_t es, uint32_t flags) {
   w.h1 = take(uf ? (size_t)s.M * 2 * s.dim * es : 0);
   w.nbr_idx = take((size_t)s.M * s.k * sizeof(int32_t));
   w.nbr_ok = take((size_t)s.M * s.k);
+  w.hsplit = simt_hsplit(s);
+  w.hpart = take(w.hsplit > 1 ? (size_t)w.hsplit * s.B * s.N * s.N * 32 * es : 0);
   w.total = o;
   return w;
 }
@@ -100,6 +110,17 @@ static int launch_pair_tiled(const PairArgs<T>& a, cudaStream_t st) {
     smem_set[dev] = smem;
   }
   dim3 grid(ceil_div(a.s.row1 - a.s.row0, 4 * PP), a.s.B);
+  if (a.hsplit > 1) {
+    PairArgs<T> a1 = a, a2 = a;
+    a1.phase = 1; a2.phase = 2;
+    dim3 g1(grid.x, grid.y, a.hsplit);
+    pair_dense_tiled_kernel<T, MP, PP><<<g1, PAIR_THREADS, smem, st>>>(a1);
+    EGNN_LAUNCH_CHECK();
+    pair_dense_tiled_kernel<T, MP, PP><<<grid, PAIR_THREADS, smem, st>>>(a2);
+    EGNN_LAUNCH_CHECK();
+    count_launch(2);
+    return EGNN_OK;
+  }
   pair_dense_tiled_kernel<T, MP, PP><<<grid, PAIR_THREADS, smem, st>>>(a);
   EGNN_LAUNCH_CHECK();
   count_launch();
@@ -155,6 +176,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   a.m_out = uf ? node_in + s.dim : nullptr;
   a.ld_m = s.dim + s.m;
   a.coors_out = uc ? static_cast<T*>(io.coors_out) : nullptr;
+  a.hpart = reinterpret_cast<T*>(base + wl.hpart); a.hsplit = wl.hsplit; a.phase = 0;
   {
     StageTimer tm(st, STAGE_PAIR);
     if (s.k > 0) {

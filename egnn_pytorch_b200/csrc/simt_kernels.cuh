@@ -156,11 +156,14 @@ gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
   for (int m = 0; m < 16; ++m) acc[m] = T(0);
   if (col < Nv) {
     const T* w = W + (size_t)col * ldw;
+    const T* arow[16];                           // row bases hoisted: RowMap costs two integer divisions
+#pragma unroll
+    for (int m = 0; m < 16; ++m) arow[m] = A + map(m < Mr ? m : 0) * lda;
     for (int k = lane; k < K; k += 32) {
       const T wv = w[k];
 #pragma unroll
       for (int m = 0; m < 16; ++m)
-        if (m < Mr) acc[m] = fma_t(A[map(m) * lda + k], wv, acc[m]);
+        if (m < Mr) acc[m] = fma_t(arow[m][k], wv, acc[m]);
     }
   }
 #pragma unroll
@@ -237,6 +240,9 @@ struct PairArgs {
   const T* packed;
   T* m_out; int ld_m;        // node_in + dim  (null when !update_feats)
   T* coors_out;              // [B,N,C]       (null when !update_coors)
+  // tiny graphs only (pair_dense_tiled_kernel): the hidden axis is split over gridDim.z CTAs in phase 1, which
+  // store partial m_pre sums to hpart [hsplit][B][N][N][MP]; phase 2 adds them up in a fixed order and finishes.
+  T* hpart; int hsplit; int phase;      // phase 0 = single pass
 };
 
 template <typename T>
@@ -535,6 +541,7 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
   }
   for (int x = tid; x < 2 * MP + 4; x += PAIR_THREADS) misc[x] = pk[a.L.misc + x];
   for (int x = tid; x < 4 * PP * RS; x += PAIR_THREADS) rows[x] = T(0);
+  __syncthreads();                                // constants visible (phase 2 never enters the chunk loop)
 
   int irow[PP];
   bool rvalid[PP], mask_i[PP];
@@ -588,7 +595,15 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
 #pragma unroll
       for (int o = 0; o < MP; ++o) acc[p][o] = T(0);
 
-    for (int c0 = 0; c0 < s.Hp; c0 += PAIR_CH) {
+    int c_begin = 0, c_end = s.Hp;
+    if (a.phase == 1) {
+      const int per = ceil_div(ceil_div(s.Hp, PAIR_CH), a.hsplit) * PAIR_CH;
+      c_begin = blockIdx.z * per;
+      c_end = min(s.Hp, c_begin + per);
+    } else if (a.phase == 2) {
+      c_end = 0;
+    }
+    for (int c0 = c_begin; c0 < c_end; c0 += PAIR_CH) {
       const int cn = min(PAIR_CH, s.Hp - c0);
       __syncthreads();
       for (int x = tid; x < cn * MP; x += PAIR_THREADS) W2s[x] = pk[a.L.w2t + (size_t)c0 * MP + x];
@@ -658,6 +673,24 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
       }
     }
 
+    if (a.phase != 0) {
+      // split hidden axis: partial sums go through global memory, summed in split order (deterministic)
+#pragma unroll
+      for (int p = 0; p < PP; ++p) {
+        if (!(rvalid[p] && jv)) continue;
+        const size_t pair = ((size_t)b * s.N + irow[p]) * s.N + j;
+        const size_t stride = (size_t)s.B * s.N * s.N * MP;
+        if (a.phase == 1) {
+#pragma unroll
+          for (int o = 0; o < MP; ++o) a.hpart[blockIdx.z * stride + pair * MP + o] = acc[p][o];
+        } else {
+          for (int z = 0; z < a.hsplit; ++z)
+#pragma unroll
+            for (int o = 0; o < MP; ++o) acc[p][o] += a.hpart[z * stride + pair * MP + o];
+        }
+      }
+      if (a.phase == 1) continue;
+    }
     // ---- epilogue of this j-tile for the PP rows
     const bool mask_j = a.has_mask ? (a.mask[(size_t)b * s.N + j] != 0) : true;
 #pragma unroll
@@ -721,7 +754,7 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
   }
 
   __syncwarp();
-  if (lane < PP && rvalid[0]) {
+  if (a.phase != 1 && lane < PP && rvalid[0]) {
     // lane p writes row p (rvalid is monotone in p)
     int p = lane;
     const int ir = s.row0 + (blockIdx.x * 4 + warp) * PP + p;
