@@ -2,5 +2,6 @@
 reference's module API (`from egnn_pytorch import EGNN, EGNN_Network`, reference
 egnn_pytorch/__init__.py:1)."""
 from .egnn import EGNN, EGNN_Network, CoorsNorm, GlobalLinearAttention  # noqa: F401
+from .graphs import GraphedForward  # noqa: F401
 
 __all__ = ["EGNN", "EGNN_Network"]

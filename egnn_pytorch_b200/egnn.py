@@ -429,23 +429,30 @@ class EGNN_Network(nn.Module):
         labels = label_emb = k_hint = None
         if exists(self.num_adj_degrees):
             assert exists(adj_mat), "adjacency matrix must be passed in (keyword argument adj_mat)"
-            n = adj_mat.shape[-1]
-            adj_in = adj_mat.ne(0).to(torch.uint8).contiguous()
-            adj_out = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
-            lab = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
-            max_sum = torch.zeros(1, dtype=torch.int32, device=dev)
-            nb = C.c_size_t()
-            nat.check("egnn_adj_workspace_bytes", lib.egnn_adj_workspace_bytes(b, n, C.byref(nb)))
-            with torch.cuda.device(dev):
-                ws = _workspace(dev, nb.value)
-                nat.check("egnn_adj_expand", lib.egnn_adj_expand(
-                    b, n, self.num_adj_degrees, _ptr(adj_in), 1 if adj_in.dim() == 3 else 0, _ptr(adj_out), _ptr(lab),
-                    _ptr(max_sum), _ptr(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            # the expansion depends on the adjacency only: cached per (storage, version), which also keeps the
+            # reference's host sync (:249) out of repeated calls and makes the forward CUDA-graph capturable
+            akey = (adj_mat.data_ptr(), adj_mat._version, tuple(adj_mat.shape), b, self.num_adj_degrees)
+            cached = self.__dict__.get("_adj_cache")
+            if cached is None or cached[0] != akey:
+                n = adj_mat.shape[-1]
+                adj_in = adj_mat.ne(0).to(torch.uint8).contiguous()
+                adj_out = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
+                lab = torch.empty((b, n, n), dtype=torch.uint8, device=dev)
+                max_sum = torch.zeros(1, dtype=torch.int32, device=dev)
+                nb = C.c_size_t()
+                nat.check("egnn_adj_workspace_bytes", lib.egnn_adj_workspace_bytes(b, n, C.byref(nb)))
+                with torch.cuda.device(dev):
+                    ws = _workspace(dev, nb.value)
+                    nat.check("egnn_adj_expand", lib.egnn_adj_expand(
+                        b, n, self.num_adj_degrees, _ptr(adj_in), 1 if adj_in.dim() == 3 else 0, _ptr(adj_out), _ptr(lab),
+                        _ptr(max_sum), _ptr(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                kmax = int(max_sum.item()) if self.layers[0][1].only_sparse_neighbors else None   # the reference's sync at :249
+                cached = (akey, adj_out, lab, kmax, adj_mat)     # adj_mat kept alive so the key cannot be recycled
+                self.__dict__["_adj_cache"] = cached
+            _, adj_out, lab, k_hint, _ = cached
             adj_mat = adj_out                                                        # layers see the expanded matrix (:428, :448)
             if exists(self.adj_emb):
                 labels, label_emb = lab, self.adj_emb.weight
-            if self.layers[0][1].only_sparse_neighbors:
-                k_hint = int(max_sum.item())                                         # the reference's sync at :249
 
         global_tokens = None
         if exists(self.global_tokens):

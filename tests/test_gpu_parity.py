@@ -175,3 +175,28 @@ def test_error_behaviour():
     layer = EGNN(dim=8, edge_dim=2).cuda()
     with pytest.raises(AssertionError):
         layer(torch.randn(1, 5, 8, device="cuda"), torch.randn(1, 5, 3, device="cuda"))   # edges missing
+
+
+@pytest.mark.parametrize("name", ["dense_mask_padded", "net_c3_small", "net_c5_small"])
+def test_cuda_graph_capture_replays_the_forward(name):
+    """egnn_pytorch_b200.GraphedForward: the whole forward is stream-ordered and sync-free, hence capturable."""
+    from egnn_pytorch_b200 import GraphedForward
+    case = cases.build_case(cases.SPECS[name])
+    mod = util.make_module(case, torch.float32)
+    ins = {k: util.to_torch(v, torch.float32, "cuda") for k, v in case["inputs"].items()}
+    if case["kind"] == "network":
+        args = (ins["feats"], ins["coors"])
+        kw = {k: ins[k] for k in ("adj_mat", "edges", "mask") if k in ins}
+    else:
+        args = (ins["feats"], ins["coors"]) + ((ins["edges"],) if "edges" in ins else ())
+        kw = {k: ins[k] for k in ("mask", "adj_mat") if k in ins}
+    eager = mod(*args, **kw)
+    fast = GraphedForward(mod, *args, **kw)
+    out = fast(*args)
+    assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+    # new coordinates through the same graph
+    x2 = args[1] * 1.25 + 0.5
+    args2 = (args[0], x2) + tuple(args[2:])
+    out2 = [t.clone() for t in fast(*args2)]
+    eager2 = mod(*args2, **kw)
+    assert torch.equal(out2[0], eager2[0]) and torch.equal(out2[1], eager2[1])
