@@ -66,7 +66,7 @@ template <typename T, int ACT, bool RES>
 static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, const T* R, int ldr, T* C,
                        int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st) {
   if (Mr <= 16) {
-    gemm_skinny_kernel<T, ACT, RES><<<ceil_div(Nout * 32, 256), 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv,
+    gemm_skinny_kernel<T, ACT, RES><<<ceil_div(ceil_div(Nout, SKINNY_COLS) * 32, 256), 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv,
                                                                             Nout, K, map);
     EGNN_LAUNCH_CHECK();
     count_launch();

@@ -144,45 +144,68 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
 // Same contract as gemm_nt_kernel for few rows (Mr <= 16, the latency-bound configs c1/README example):
 // one warp per output column n reads W[n, :] once, coalesced, and keeps all Mr row sums in registers.
 // =====================================================================================
+constexpr int SKINNY_COLS = 4;      // output columns per warp: every A value loaded feeds 4 FMAs
+
 template <typename T, int ACT, bool RES>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
                    const T* __restrict__ bias, const T* __restrict__ R, int ldr,
                    T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map) {
-  const int col = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
-  if (col >= Nout) return;
-  T acc[16];
+  const int col0 = ((blockIdx.x * blockDim.x + threadIdx.x) / 32) * SKINNY_COLS, lane = threadIdx.x % 32;
+  if (col0 >= Nout) return;
+  T acc[16][SKINNY_COLS];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) acc[m] = T(0);
-  if (col < Nv) {
-    const T* w = W + (size_t)col * ldw;
-    const T* arow[16];                           // row bases hoisted: RowMap costs two integer divisions
+  for (int m = 0; m < 16; ++m)
 #pragma unroll
-    for (int m = 0; m < 16; ++m) arow[m] = A + map(m < Mr ? m : 0) * lda;
-    for (int k = lane; k < K; k += 32) {
-      const T wv = w[k];
+    for (int n = 0; n < SKINNY_COLS; ++n) acc[m][n] = T(0);
+  const T* arow[16];                             // row bases hoisted: RowMap costs two integer divisions
 #pragma unroll
-      for (int m = 0; m < 16; ++m)
-        if (m < Mr) acc[m] = fma_t(arow[m][k], wv, acc[m]);
+  for (int m = 0; m < 16; ++m) arow[m] = A + map(m < Mr ? m : 0) * lda;
+  const T* wrow[SKINNY_COLS];
+#pragma unroll
+  for (int n = 0; n < SKINNY_COLS; ++n) wrow[n] = W + (size_t)min(col0 + n, Nv - 1) * ldw;
+#pragma unroll 2
+  for (int k = lane; k < K; k += 32) {
+    T wv[SKINNY_COLS];
+#pragma unroll
+    for (int n = 0; n < SKINNY_COLS; ++n) wv[n] = wrow[n][k];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      if (m < Mr) {
+        const T av = arow[m][k];
+#pragma unroll
+        for (int n = 0; n < SKINNY_COLS; ++n) acc[m][n] = fma_t(av, wv[n], acc[m][n]);
+      }
     }
   }
 #pragma unroll
   for (int m = 0; m < 16; ++m)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[m] += shfl_xor_t<T>(acc[m], o);
-  if (lane < Mr) {
+    for (int n = 0; n < SKINNY_COLS; ++n)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[m][n] += shfl_xor_t<T>(acc[m][n], o);
+  // lane = (row m, column n) for the first 16*4 = 64 results: two passes of 32 lanes
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int m = pass * 8 + lane / SKINNY_COLS, n = lane % SKINNY_COLS;
     T v = T(0);
 #pragma unroll
-    for (int m = 0; m < 16; ++m) if (m == lane) v = acc[m];
-    const size_t row = map(lane);
-    if (col < Nv) {
-      v += bias ? bias[col] : T(0);
-      if (ACT == 1) v = silu_acc<T>(v);
-      if (RES) v += R[row * ldr + col];
-    } else {
-      v = T(0);
+    for (int mm = 0; mm < 16; ++mm)
+#pragma unroll
+      for (int nn = 0; nn < SKINNY_COLS; ++nn)
+        if (mm == m && nn == n) v = acc[mm][nn];
+    const int col = col0 + n;
+    if (m < Mr && col < Nout) {
+      const size_t row = map(m);
+      if (col < Nv) {
+        v += bias ? bias[col] : T(0);
+        if (ACT == 1) v = silu_acc<T>(v);
+        if (RES) v += R[row * ldr + col];
+      } else {
+        v = T(0);
+      }
+      Cout[row * ldo + col] = v;
     }
-    Cout[row * ldo + col] = v;
   }
 }
 

@@ -18,6 +18,7 @@ g = torch.Generator().manual_seed(1)
 cfgs = {
     "c4": (dict(dim=256, edge_dim=4, num_nearest_neighbors=32), 8, 4096),
     "c2": (dict(dim=512), 4, 1024),
+    "c1": (dict(dim=512), 1, 16),
     "c3layer": (dict(dim=32, num_nearest_neighbors=8, norm_feats=True, coor_weights_clamp_value=2.0), 1, 1024),
 }
 kw, B, N = cfgs[name]
@@ -32,7 +33,7 @@ for _ in range(3):
 torch.cuda.synchronize()
 lib.egnn_profile_read(None, None, None, 1)
 lib.egnn_profile_enable(1)
-iters = 10
+iters = 50
 for _ in range(iters):
     mod(*args)
 torch.cuda.synchronize()
