@@ -147,7 +147,10 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   const RowMap ident{s.N, s.N, 0};
 
   // 1. neighbour lists (egnn_pytorch.py:237-260)
-  if (s.k > 0) {
+  if (s.k > 0 && io.nbr_idx) {                       // edge-list mode: the caller's lists, no ranking
+    nbr_idx = const_cast<int32_t*>(io.nbr_idx);
+    nbr_ok = nullptr;
+  } else if (s.k > 0) {
     StageTimer tm(st, STAGE_SELECT);
     count_launch();
     const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;     // :250
@@ -330,13 +333,14 @@ extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLaye
   const size_t nl = hio->edge_labels ? (size_t)s.M * s.N : 0;
   const size_t nm = hio->mask ? (size_t)s.M : 0;
   const size_t na = hio->adj ? (size_t)((desc->flags & EGNN_FLAG_ADJ_BATCHED) ? s.B : 1) * s.N * s.N : 0;
+  const size_t nn = hio->nbr_idx ? (size_t)s.M * s.k * sizeof(int32_t) : 0;
   size_t wsb = 0;
   EGNN_TRY(egnn_layer_workspace_bytes(desc, &wsb));
   // one device arena: [feats | feats_out | coors | coors_out | edges | labels | mask | adj | workspace]
   size_t off[10];
   size_t o = 0;
-  const size_t sizes[9] = {nf, nf, nc, nc, ne, nl, nm, na, wsb};
-  for (int i = 0; i < 9; ++i) { off[i] = o; o += round_up(sizes[i], 256); }
+  const size_t sizes[10] = {nf, nf, nc, nc, ne, nl, nm, na, wsb, nn};
+  for (int i = 0; i < 10; ++i) { off[i] = o; o += round_up(sizes[i], 256); }
   char* arena = nullptr;
   EGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&arena), o + 256, st));
   int rc = EGNN_OK;
@@ -347,7 +351,7 @@ extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLaye
     }
   };
   h2d(0, hio->feats, nf); h2d(2, hio->coors, nc); h2d(4, hio->edges, ne); h2d(5, hio->edge_labels, nl);
-  h2d(6, hio->mask, nm); h2d(7, hio->adj, na);
+  h2d(6, hio->mask, nm); h2d(7, hio->adj, na); h2d(9, hio->nbr_idx, nn);
   if (rc == EGNN_OK) {
     EgnnLayerIO dio;
     dio.feats = arena + off[0]; dio.feats_out = arena + off[1];
@@ -356,6 +360,7 @@ extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLaye
     dio.edge_labels = nl ? reinterpret_cast<uint8_t*>(arena + off[5]) : nullptr;
     dio.mask = nm ? reinterpret_cast<uint8_t*>(arena + off[6]) : nullptr;
     dio.adj = na ? reinterpret_cast<uint8_t*>(arena + off[7]) : nullptr;
+    dio.nbr_idx = nn ? reinterpret_cast<int32_t*>(arena + off[9]) : nullptr;
     rc = egnn_layer_forward(desc, w, packed, &dio, arena + off[8], wsb, stream);
   }
   if (rc == EGNN_OK) {

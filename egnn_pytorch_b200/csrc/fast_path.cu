@@ -294,7 +294,10 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
   } else {         // neighbour lists: distance + top-k select, then the gathered fused edge kernel
     int32_t* nbr_idx = reinterpret_cast<int32_t*>(base + wl.nbr_idx);
     uint8_t* nbr_ok = base + wl.nbr_ok;
-    {
+    if (io.nbr_idx) {                                  // edge-list mode: the caller's lists, no ranking
+      nbr_idx = const_cast<int32_t*>(io.nbr_idx);
+      nbr_ok = nullptr;
+    } else {
       StageTimer tm(st, STAGE_SELECT);
       const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;
       EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, 3, s.k, io.coors, io.mask, io.adj,

@@ -329,14 +329,15 @@ pair_kernel(const PairArgs<T> a) {
 
   for (int s0 = 0; s0 < J; s0 += TS) {
     const int sidx = s0 + sl;
-    const bool pair_valid = row_valid && sidx < J;
+    bool pair_valid = row_valid && sidx < J;
     int j = 0;
     bool ok = true;
     if (KNN) {
       if (pair_valid) {
         size_t o = ((size_t)b * s.N + i) * s.k + sidx;
         j = a.nbr_idx[o];
-        ok = a.nbr_ok[o] != 0;
+        ok = a.nbr_ok ? a.nbr_ok[o] != 0 : true;
+        if (j < 0) { j = 0; pair_valid = false; }      // empty slot of a caller-supplied neighbour list
       }
     } else {
       j = pair_valid ? sidx : 0;

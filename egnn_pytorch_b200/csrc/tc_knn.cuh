@@ -121,12 +121,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   const bool mask_i = iv && (a.has_mask ? a.mask[nodei] != 0 : true);
 
   // ---- pair mapping: lane = neighbour slot
-  const bool sv = iv && lane < K;
+  bool sv = iv && lane < K;
   int j = i;
   bool okj = true;
   if (sv) {
     j = a.nbr_idx[nodei * K + lane];
-    okj = a.nbr_ok[nodei * K + lane] != 0;
+    okj = a.nbr_ok ? a.nbr_ok[nodei * K + lane] != 0 : true;
+    if (j < 0) { j = i; sv = false; }                 // empty slot of a caller-supplied neighbour list
   }
   const size_t nodej = (size_t)b * N + j;
   const float r0 = xi0 - a.coors[nodej * 3 + 0], r1 = xi1 - a.coors[nodej * 3 + 1], r2 = xi2 - a.coors[nodej * 3 + 2];

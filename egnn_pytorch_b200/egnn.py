@@ -32,7 +32,7 @@ import torch.nn.functional as F
 
 from . import _native as nat
 
-__all__ = ["EGNN", "EGNN_Network", "CoorsNorm", "GlobalLinearAttention"]
+__all__ = ["EGNN", "EGNN_Network", "CoorsNorm", "GlobalLinearAttention", "edge_index_to_neighbors"]
 
 
 def exists(v):
@@ -205,8 +205,13 @@ class EGNN(nn.Module):
 
     # -------------------------------------------------------------- forward
     @torch.no_grad()
-    def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, *, _edge_labels=None, _label_emb=None,
-                _k_hint=None, _rows=None):
+    def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, *, neighbors=None, _edge_labels=None,
+                _label_emb=None, _k_hint=None, _rows=None):
+        """Reference signature `forward(feats, coors, edges=None, mask=None, adj_mat=None)` (egnn_pytorch.py:224).
+
+        `neighbors` (additive, keyword-only): int tensor [B, N, k] of neighbour indices, -1 = empty slot.  When
+        given, the layer runs on exactly these edges and the O(N^2) distance / top-k pass is skipped -- the
+        edge-list mode of SURVEY.md section 8(f) (`edge_index_to_neighbors` converts a PyG-style edge_index)."""
         if self.training and self.dropout_p > 0:
             raise NotImplementedError("dropout in training mode is outside this forward-only build")
         lib = nat.load()
@@ -223,7 +228,14 @@ class EGNN(nn.Module):
         adj_u8 = None
         k = 0
         flags = self._flags()
-        if use_nearest:
+        nbr = None
+        if neighbors is not None:
+            assert neighbors.dim() == 3 and neighbors.shape[:2] == (b, n), "neighbors must be [B, N, k]"
+            nbr = neighbors.to(device=dev, dtype=torch.int32).contiguous()
+            k = nbr.shape[-1]
+            if not (0 < k <= n):
+                raise RuntimeError(f"neighbour lists need 0 < k <= N, got k={k}, N={n}")
+        elif use_nearest:
             k = self.num_nearest_neighbors
             if exists(adj_mat):
                 adj_u8 = _as_u8(adj_mat, dev)
@@ -241,17 +253,17 @@ class EGNN(nn.Module):
             kdt = torch.float32
         try:
             return self._run(lib, dev, kdt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
-                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
+                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
         except nat.EgnnNativeError as e:
             if e.code != nat.ERR_UNSUPPORTED or kdt != torch.bfloat16:
                 raise
         # the tensor-core kernels do not cover this option set: fp32 SIMT kernels (still on the GPU); remembered
         self._tc_unsupported.add(cfg_key)
         return self._run(lib, dev, torch.float32, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
-                         b, n, c, k, flags, cont_edge_dim, label_dim, _rows)
+                         b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
 
     def _run(self, lib, dev, kdt, feats, coors, edges, mask, adj_u8, labels, label_emb, b, n, c, k, flags,
-             cont_edge_dim, label_dim, rows):
+             cont_edge_dim, label_dim, rows, nbr=None):
         cdt = torch.float64 if kdt == torch.float64 else torch.float32
         st = self._staged(dev, kdt)
         T = dict(st["tensors"])
@@ -313,13 +325,31 @@ class EGNN(nn.Module):
                              edge_labels=None if l_in is None else l_in.data_ptr(),
                              mask=None if m_in is None else m_in.data_ptr(),
                              adj=None if adj_u8 is None else adj_u8.data_ptr(),
-                             feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr())
+                             feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr(),
+                             nbr_idx=None if nbr is None else nbr.data_ptr())
             ws = _workspace(dev, ws_bytes)
             nat.check("egnn_layer_forward",
                       lib.egnn_layer_forward(C.byref(desc), C.byref(w), _ptr(packed), C.byref(io), _ptr(ws),
                                              ws.numel(), stream))
         self.last_path = {torch.float64: "fp64-simt", torch.float32: "fp32-simt", torch.bfloat16: "bf16-tcgen05"}[kdt]
         return (f_out.to(device=feats.device, dtype=feats.dtype), x_out.to(device=coors.device, dtype=coors.dtype))
+
+
+def edge_index_to_neighbors(edge_index, num_nodes, k=None):
+    """PyG-style `edge_index` [2, E] (messages flow source j = edge_index[0] -> target i = edge_index[1], one graph)
+    -> padded neighbour lists [1, N, k] for `EGNN.forward(..., neighbors=...)`; -1 marks empty slots.  Glue code:
+    a stable sort by target node, nothing on the hot path."""
+    src, dst = edge_index[0].long(), edge_index[1].long()
+    order = torch.argsort(dst, stable=True)
+    src, dst = src[order], dst[order]
+    deg = torch.bincount(dst, minlength=num_nodes)
+    kmax = int(deg.max().item()) if k is None else k
+    start = torch.cumsum(deg, 0) - deg
+    slot = torch.arange(src.numel(), device=src.device) - start[dst]
+    out = torch.full((num_nodes, kmax), -1, dtype=torch.int32, device=src.device)
+    keep = slot < kmax
+    out[dst[keep], slot[keep]] = src[keep].to(torch.int32)
+    return out.unsqueeze(0)
 
 
 # ----------------------------------------------------------------------------- global attention (PyTorch glue)

@@ -122,6 +122,9 @@ typedef struct EgnnLayerIO {
                                 only read when k > 0                                      */
   void*          feats_out;  /* [B, N, dim]                                               */
   void*          coors_out;  /* [B, N, C]                                                 */
+  const int32_t* nbr_idx;    /* optional, k > 0 only: caller-supplied neighbour lists [B, N, k] (edge-list
+                                mode): the distance/top-k pass is skipped.  An entry
+                                < 0 is an empty slot and never contributes.  NULL = select as the reference does. */
 } EgnnLayerIO;
 
 int         egnn_abi_version(void);

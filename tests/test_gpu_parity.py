@@ -200,3 +200,38 @@ def test_cuda_graph_capture_replays_the_forward(name):
     out2 = [t.clone() for t in fast(*args2)]
     eager2 = mod(*args2, **kw)
     assert torch.equal(out2[0], eager2[0]) and torch.equal(out2[1], eager2[1])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_edge_list_mode_matches_the_select_path(dtype):
+    """`neighbors=`: (1) the lists egnn_knn_select would pick reproduce the kNN forward bit for bit; (2) a chain given
+    as an edge_index (with -1 padding at the ends) equals `only_sparse_neighbors` on the chain adjacency."""
+    import ctypes as C
+    from egnn_pytorch_b200 import EGNN, edge_index_to_neighbors, _native as nat
+    lib = nat.load()
+    torch.manual_seed(0)
+    B, N, d, k = 2, 60, 64, 6
+    feats = torch.randn(B, N, d, device="cuda").to(dtype)
+    coors = torch.randn(B, N, 3, device="cuda")
+    mask = torch.ones(B, N, dtype=torch.bool, device="cuda")
+    layer = EGNN(dim=d, num_nearest_neighbors=k).to(dtype).cuda().eval()
+    f0, x0 = layer(feats, coors, mask=mask)
+    idx = torch.empty(B, N, k, dtype=torch.int32, device="cuda")
+    rc = lib.egnn_knn_select(nat.DTYPE_F32, B, N, 3, k, C.c_void_p(coors.data_ptr()), None, None, 0, float("inf"),
+                             C.c_void_p(idx.data_ptr()), None, None)
+    assert rc == 0
+    f1, x1 = layer(feats, coors, mask=mask, neighbors=idx)
+    assert torch.equal(f0, f1) and torch.equal(x0, x1)
+    # chain graph as an edge list
+    i = torch.arange(N, device="cuda")
+    src = torch.cat([i, i[:-1], i[1:]]); dst = torch.cat([i, i[1:], i[:-1]])        # self, i-1 -> i, i+1 -> i
+    nbrs = edge_index_to_neighbors(torch.stack([src, dst]), N).expand(B, -1, -1)
+    assert nbrs.shape[-1] == 3 and int((nbrs < 0).sum()) == 2 * B
+    sparse = EGNN(dim=d, only_sparse_neighbors=True).to(dtype).cuda().eval()
+    sparse.load_state_dict(layer.state_dict())
+    adj = (i[:, None] - i[None, :]).abs() <= 1
+    f2, x2 = sparse(feats, coors, mask=mask, adj_mat=adj)
+    f3, x3 = layer(feats, coors, mask=mask, neighbors=nbrs)
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-5          # same edges, different slot order -> different summation order
+    assert float((f2.float() - f3.float()).abs().max()) <= tol * float(f2.float().abs().max())
+    assert float((x2 - x3).abs().max()) <= tol
