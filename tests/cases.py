@@ -263,3 +263,44 @@ SPECS = {
     "net_adj_random":     dict(kind=NW, cfg=dict(depth=2, dim=12, num_adj_degrees=2, adj_dim=3, only_sparse_neighbors=True),
                                B=2, N=16, seed=57, init="xavier", adj="random3d", adj_p=0.1, mask="full"),
 }
+
+
+# ------------------------------------------------------------------ gradients (backward parity)
+#
+# Loss = sum(feats_out * G_f) + sum(coors_out * G_x) with fixed random cotangents G_f, G_x, so one
+# backward pass exercises every output element.  The huge-parameter c1 cases are left out of the committed
+# gradient fixtures (25 MB each in float64); they are still checked CUDA-vs-oracle.
+
+GRAD_SPECS = [n for n in SPECS if not n.startswith("c1_") and n not in {"knn_k33", "knn_k32_c5"}]
+
+
+def upstream_grads(case):
+    """Deterministic cotangents for (feats_out, coors_out)."""
+    spec = case["spec"]
+    rs = np.random.RandomState(spec["seed"] + 100003)
+    B, N, C = spec["B"], spec["N"], spec.get("C", 3)
+    d = case["ncfg"]["dim"] if case["kind"] == "network" else case["cfg"]["dim"]
+    return rs.standard_normal((B, N, d)), rs.standard_normal((B, N, C))
+
+
+def run_oracle_grad(case):
+    """-> dict(feats|None, coors, edges|None, params{key: grad}) from the numpy backward oracle."""
+    from oracle import egnn_oracle_grad as G
+    ins = case["inputs"]
+    gf, gx = upstream_grads(case)
+    if case["kind"] == "network":
+        return G.egnn_network_backward(case["params"], case["ncfg"], ins["feats"], ins["coors"], ins.get("adj_mat"),
+                                       ins.get("edges"), ins.get("mask"), gf, gx)
+    return G.egnn_layer_backward(case["params"], case["cfg"], ins["feats"], ins["coors"], ins.get("edges"),
+                                 ins.get("mask"), ins.get("adj_mat"), gf, gx)
+
+
+def flatten_grads(r):
+    """dict from run_oracle_grad / the fixtures -> flat {name: array} ('in.feats', 'in.coors', 'in.edges', 'p.<key>')."""
+    out = {}
+    for k in ("feats", "coors", "edges"):
+        if r.get(k) is not None:
+            out[f"in.{k}"] = np.asarray(r[k])
+    for k, v in r["params"].items():
+        out[f"p.{k}"] = np.asarray(v)
+    return out

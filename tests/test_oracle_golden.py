@@ -9,7 +9,8 @@ import pytest
 import cases
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+NAMES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+               if not n.startswith("grad_"))
 
 
 def test_every_spec_has_a_fixture():
@@ -56,3 +57,51 @@ def test_oracle_equivariance_fp64():
     f1, c1 = cases.run_oracle(dict(case, inputs=ins_r))
     assert np.abs(f1 - f2).max() < 1e-12
     assert np.abs(c1 - (c2 @ q + t)).max() < 1e-12
+
+
+# ---------------------------------------------------------------- backward oracle (oracle/egnn_oracle_grad.py)
+
+
+def test_every_grad_spec_has_a_fixture():
+    have = {os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(GOLDEN, "grad_*.npz"))}
+    assert have == set(cases.GRAD_SPECS), have ^ set(cases.GRAD_SPECS)
+
+
+@pytest.mark.parametrize("name", cases.GRAD_SPECS)
+def test_grad_oracle_matches_reference_autograd_fp64(name):
+    g = np.load(os.path.join(GOLDEN, f"grad_{name}.npz"))
+    case = cases.build_case(cases.SPECS[name])
+    assert cases.case_checksum(case) == str(g["checksum"])
+    if bool(g["tie_dependent"]):
+        pytest.skip("reference gradients depend on torch.topk's tie order")
+    mine = cases.flatten_grads(cases.run_oracle_grad(case))
+    keys = {k for k in g.files if k.startswith(("in.", "p."))}
+    assert keys == set(mine)
+    # CoorsNorm divides the self pair (|x_i - x_i| = 0) by eps = 1e-8: +-7e7-sized terms cancel in both
+    # implementations and leave ~1e-9 of rounding noise; everything else agrees to summation order.
+    tol = 1e-7 if "norm_coors" in str(case["spec"]["cfg"]) else 1e-11
+    for k in sorted(keys):
+        scale = max(1.0, float(np.abs(g[k]).max()))
+        assert np.abs(mine[k] - g[k]).max() <= tol * scale, k
+
+
+def test_grad_oracle_against_finite_differences():
+    """Independent of the fixtures: directional derivative of the FORWARD oracle by central differences."""
+    case = cases.build_case(cases.SPECS["knn_edges_mask"])
+    gf, gx = cases.upstream_grads(case)
+    grads = cases.flatten_grads(cases.run_oracle_grad(case))
+    rs = np.random.RandomState(7)
+
+    def loss(c):
+        f, x = cases.run_oracle(c)
+        return float((f * gf).sum() + (x * gx).sum())
+
+    for group, prefix in (("inputs", "in."), ("params", "p.")):
+        for key in [k[len(prefix):] for k in grads if k.startswith(prefix)]:
+            v = rs.standard_normal(np.shape(case[group][key]))
+            eps = 1e-6
+            hi = dict(case, **{group: dict(case[group], **{key: case[group][key] + eps * v})})
+            lo = dict(case, **{group: dict(case[group], **{key: case[group][key] - eps * v})})
+            fd = (loss(hi) - loss(lo)) / (2 * eps)
+            an = float((grads[prefix + key] * v).sum())
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (key, fd, an)
