@@ -36,6 +36,8 @@ for p in (REPO, os.path.join(REPO, "tests")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+torch.set_grad_enabled(False)      # forward benchmark: no autograd state is kept
+
 WORKLOADS = {
     # BASELINE.json configs[1]
     "c2": dict(kind="layer", cfg=dict(dim=512), B=4, N=1024, C=3, label="EGNN(dim=512) dense all-pairs B=4 N=1024"),

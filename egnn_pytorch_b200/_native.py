@@ -70,6 +70,15 @@ class LayerIO(C.Structure):
     ]
 
 
+class LayerWeightGrads(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in WEIGHT_FIELDS]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [("g_feats_out", C.c_void_p), ("g_coors_out", C.c_void_p), ("g_feats", C.c_void_p),
+                ("g_coors", C.c_void_p), ("g_edges", C.c_void_p), ("w", LayerWeightGrads)]
+
+
 # every symbol include/egnn_b200.h declares: (restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
@@ -81,6 +90,9 @@ SYMBOLS = {
     "egnn_layer_forward": (C.c_int, [_P(LayerDesc), _P(LayerWeights), C.c_void_p, _P(LayerIO), C.c_void_p,
                                      C.c_size_t, C.c_void_p]),
     "egnn_layer_forward_host": (C.c_int, [_P(LayerDesc), _P(LayerWeights), C.c_void_p, _P(LayerIO), C.c_void_p]),
+    "egnn_layer_backward_workspace_bytes": (C.c_int, [_P(LayerDesc), _P(C.c_size_t)]),
+    "egnn_layer_backward": (C.c_int, [_P(LayerDesc), _P(LayerWeights), C.c_void_p, _P(LayerIO), C.c_void_p,
+                                      _P(LayerGrads), C.c_void_p, C.c_size_t, C.c_void_p]),
     "egnn_knn_select": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "egnn_adj_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_size_t)]),

@@ -29,7 +29,7 @@ namespace egnn {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t round_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
-inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
+__host__ __device__ inline int round_up_i(int a, int b) { return (a + b - 1) / b * b; }
 
 // ------------------------------------------------------------------ derived sizes
 struct Dims {

@@ -18,7 +18,10 @@ Element type -> kernel family
                            fp32 SIMT kernels instead (still on the GPU; see `last_path`).
 `precision='fast'` / `'accurate'` overrides the choice for fp32/bf16 parameters.
 
-Forward only in this round: outputs carry no autograd graph.
+Training: when autograd is recording and an input or parameter requires grad, the layer runs as a
+`torch.autograd.Function` whose backward is `egnn_layer_backward` -- hand-written recompute-in-backward
+kernels (fp32 / fp64; bf16 modules train through the fp32 kernels).  Under `torch.no_grad()` /
+`requires_grad_(False)` nothing is saved and the fastest kernels are used.
 """
 from __future__ import annotations
 
@@ -114,6 +117,51 @@ def _mlp(d_in, d_hidden, d_out, dropout, final_act=False):
     return nn.Sequential(*mods)
 
 
+# ----------------------------------------------------------------------------- autograd bridge
+
+
+class _EGNNLayerFunction(torch.autograd.Function):
+    """forward = egnn_layer_forward on a private workspace that is kept for backward;
+    backward = egnn_layer_backward (what autograd derives from reference egnn_pytorch.py:224-341)."""
+
+    @staticmethod
+    def forward(ctx, run, feats, coors, edges, label_emb, *params):
+        f_out, x_out, saved = run()
+        ctx.saved = saved
+        ctx.meta = [(t.dtype, t.device) if t is not None else None for t in (feats, coors, edges, label_emb) + params]
+        return f_out, x_out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_f, g_x):
+        sv = ctx.saved
+        lib, dev, kdt, cdt = nat.load(), sv["dev"], sv["kdt"], sv["cdt"]
+        T = sv["tensors"]
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            g_f, g_x = _as(g_f, dev, kdt), _as(g_x, dev, cdt)
+            gw = {f: torch.empty_like(T[f]) for f in nat.WEIGHT_FIELDS if f in T}
+            g_feats, g_coors = torch.empty_like(sv["f_in"]), torch.empty_like(sv["x_in"])
+            g_edges = torch.empty_like(sv["e_in"]) if (sv["e_in"] is not None and ctx.needs_input_grad[3]) else None
+            grads = nat.LayerGrads(g_feats_out=g_f.data_ptr(), g_coors_out=g_x.data_ptr(), g_feats=g_feats.data_ptr(),
+                                   g_coors=g_coors.data_ptr(), g_edges=None if g_edges is None else g_edges.data_ptr(),
+                                   w=nat.LayerWeightGrads(**{f: t.data_ptr() for f, t in gw.items()}))
+            nb = C.c_size_t()
+            nat.check("egnn_layer_backward_workspace_bytes",
+                      lib.egnn_layer_backward_workspace_bytes(C.byref(sv["desc"]), C.byref(nb)))
+            ws = _workspace(dev, nb.value)
+            nat.check("egnn_layer_backward",
+                      lib.egnn_layer_backward(C.byref(sv["desc"]), C.byref(sv["w"]), _ptr(sv["packed"]), C.byref(sv["io"]),
+                                              _ptr(sv["ws"]), C.byref(grads), _ptr(ws), ws.numel(), stream))
+        ctx.saved = None
+        back = lambda g, m: None if (g is None or m is None) else g.to(device=m[1], dtype=m[0])
+        out = [None, back(g_feats, ctx.meta[0]), back(g_coors, ctx.meta[1]), back(g_edges, ctx.meta[2]),
+               back(gw.get("label_emb"), ctx.meta[3])]
+        for f, m in zip(sv["param_fields"], ctx.meta[4:]):
+            out.append(back(gw.get(f), m))
+        return tuple(g if need else None for g, need in zip(out, ctx.needs_input_grad))
+
+
 # ----------------------------------------------------------------------------- the layer
 
 
@@ -204,7 +252,6 @@ class EGNN(nn.Module):
         return torch.float32
 
     # -------------------------------------------------------------- forward
-    @torch.no_grad()
     def forward(self, feats, coors, edges=None, mask=None, adj_mat=None, *, neighbors=None, _edge_labels=None,
                 _label_emb=None, _k_hint=None, _rows=None):
         """Reference signature `forward(feats, coors, edges=None, mask=None, adj_mat=None)` (egnn_pytorch.py:224).
@@ -213,13 +260,39 @@ class EGNN(nn.Module):
         given, the layer runs on exactly these edges and the O(N^2) distance / top-k pass is skipped -- the
         edge-list mode of SURVEY.md section 8(f) (`edge_index_to_neighbors` converts a PyG-style edge_index)."""
         if self.training and self.dropout_p > 0:
-            raise NotImplementedError("dropout in training mode is outside this forward-only build")
+            raise NotImplementedError("dropout in training mode is not implemented (SURVEY.md section 8(f) rank 4)")
+        fields = self._state_fields()
+        train = torch.is_grad_enabled() and (
+            feats.requires_grad or coors.requires_grad or (edges is not None and edges.requires_grad) or
+            (_label_emb is not None and _label_emb.requires_grad) or any(p.requires_grad for _, _, _, p in fields))
+        if train:
+            return self._forward_train(fields, feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb,
+                                       _k_hint, _rows)
+        with torch.no_grad():
+            return self._forward_impl(feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb, _k_hint,
+                                      _rows)
+
+    def _forward_train(self, fields, feats, coors, edges, mask, adj_mat, neighbors, labels, label_emb, k_hint, rows):
+        if rows is not None:
+            raise NotImplementedError("a row range cannot be differentiated; shard the batch instead")
+        params = [p for _, _, _, p in fields]
+
+        def run():
+            return self._forward_impl(feats, coors, edges, mask, adj_mat, neighbors, labels, label_emb, k_hint, None,
+                                      train=True, param_fields=[f for _, _, f, _ in fields])
+
+        return _EGNNLayerFunction.apply(run, feats, coors, edges, label_emb, *params)
+
+    def _forward_impl(self, feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb, _k_hint, _rows,
+                      train=False, param_fields=None):
         lib = nat.load()
         dev = _compute_device(feats)
         b, n, d = feats.shape
         assert d == self.dim, f"feature width {d} != dim {self.dim}"
         c = coors.shape[-1]
         kdt = self._kernel_dtype()
+        if train and kdt == torch.bfloat16:
+            kdt = torch.float32                 # the tensor-core kernels are forward-only
         label_dim = 0 if _label_emb is None else _label_emb.shape[1]
         cont_edge_dim = self.edge_dim - label_dim
         assert (edges is None) == (cont_edge_dim == 0), "edges must be given iff edge_dim > 0"
@@ -253,7 +326,7 @@ class EGNN(nn.Module):
             kdt = torch.float32
         try:
             return self._run(lib, dev, kdt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
-                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
+                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr, train, param_fields)
         except nat.EgnnNativeError as e:
             if e.code != nat.ERR_UNSUPPORTED or kdt != torch.bfloat16:
                 raise
@@ -263,7 +336,7 @@ class EGNN(nn.Module):
                          b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
 
     def _run(self, lib, dev, kdt, feats, coors, edges, mask, adj_u8, labels, label_emb, b, n, c, k, flags,
-             cont_edge_dim, label_dim, rows, nbr=None):
+             cont_edge_dim, label_dim, rows, nbr=None, train=False, param_fields=None):
         cdt = torch.float64 if kdt == torch.float64 else torch.float32
         st = self._staged(dev, kdt)
         T = dict(st["tensors"])
@@ -327,12 +400,19 @@ class EGNN(nn.Module):
                              adj=None if adj_u8 is None else adj_u8.data_ptr(),
                              feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr(),
                              nbr_idx=None if nbr is None else nbr.data_ptr())
-            ws = _workspace(dev, ws_bytes)
+            # training keeps the workspace (per-node tables, pooled messages, neighbour lists) for backward
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if train else _workspace(dev, ws_bytes)
             nat.check("egnn_layer_forward",
                       lib.egnn_layer_forward(C.byref(desc), C.byref(w), _ptr(packed), C.byref(io), _ptr(ws),
                                              ws.numel(), stream))
         self.last_path = {torch.float64: "fp64-simt", torch.float32: "fp32-simt", torch.bfloat16: "bf16-tcgen05"}[kdt]
-        return (f_out.to(device=feats.device, dtype=feats.dtype), x_out.to(device=coors.device, dtype=coors.dtype))
+        outs = (f_out.to(device=feats.device, dtype=feats.dtype), x_out.to(device=coors.device, dtype=coors.dtype))
+        if not train:
+            return outs
+        saved = dict(dev=dev, kdt=kdt, cdt=cdt, desc=desc, w=w, packed=packed, io=io, ws=ws, tensors=T,
+                     f_in=f_in, x_in=x_in, e_in=e_in, param_fields=param_fields,
+                     keep=(m_in, l_in, adj_u8, nbr, lab_w))            # everything io points at stays alive
+        return outs + (saved,)
 
 
 def edge_index_to_neighbors(edge_index, num_nodes, k=None):
@@ -432,7 +512,6 @@ class EGNN_Network(nn.Module):
                 EGNN(dim=dim, edge_dim=edge_dim + adj_dim, norm_feats=True, **kwargs),
             ]))
 
-    @torch.no_grad()
     def forward(self, feats, coors, adj_mat=None, edges=None, mask=None, return_coor_changes=False):
         lib = nat.load()
         out_dev = coors.device

@@ -155,6 +155,35 @@ int egnn_layer_forward(const EgnnLayerDesc* desc, const EgnnLayerWeights* w, con
 int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLayerWeights* w,
                             const void* packed, const EgnnLayerIO* host_io, void* stream);
 
+/*
+ * Backward of one layer: what autograd computes through the reference's
+ * EGNN.forward (egnn_pytorch.py:224-341).  fp32 / fp64 kernels only (EGNN_ERR_UNSUPPORTED for bf16 and for a row
+ * range).  The edge step is recomputed pair by pair, so the only saved state is the forward WORKSPACE:
+ * `fwd_workspace` must be the buffer egnn_layer_forward ran on with the same desc / io, unmodified since.
+ * Gradient buffers are OVERWRITTEN (not accumulated into).  Neighbour selection contributes no gradient.
+ */
+typedef struct EgnnLayerWeightGrads {   /* one buffer per EgnnLayerWeights field, same shape and dtype; NULL for
+                                           modules the flags disable */
+  void* edge_w1; void* edge_b1; void* edge_w2; void* edge_b2; void* gate_w; void* gate_b;
+  void* norm_g; void* norm_b; void* coors_scale;
+  void* node_w1; void* node_b1; void* node_w2; void* node_b2;
+  void* coors_w1; void* coors_b1; void* coors_w2; void* coors_b2; void* label_emb;
+} EgnnLayerWeightGrads;
+
+typedef struct EgnnLayerGrads {
+  const void* g_feats_out;   /* [B, N, dim]  dL/d feats_out (input)                         */
+  const void* g_coors_out;   /* [B, N, C]    dL/d coors_out (input)                         */
+  void*       g_feats;       /* [B, N, dim]  dL/d feats                                     */
+  void*       g_coors;       /* [B, N, C]    dL/d coors                                     */
+  void*       g_edges;       /* [B, N, N, edge_dim] dL/d edges, or NULL (not wanted / edge_dim == 0) */
+  EgnnLayerWeightGrads w;
+} EgnnLayerGrads;
+
+int egnn_layer_backward_workspace_bytes(const EgnnLayerDesc* desc, size_t* out_bytes);
+int egnn_layer_backward(const EgnnLayerDesc* desc, const EgnnLayerWeights* w, const void* packed,
+                        const EgnnLayerIO* io, const void* fwd_workspace, const EgnnLayerGrads* grads,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Neighbour selection alone == ranking + topk of egnn_pytorch.py:237-260: for every node the k
  * lowest-ranked nodes (rank = squared distance; 1e5 if either end is masked out; -1 self and 0
  * adjacent when `adj` is given), ascending, ties to the lowest index.

@@ -27,3 +27,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _inference_mode_by_default():
+    """The parity tests are forward-only: run them with autograd off (as inference callers do) so the fastest
+    kernels are selected; the gradient tests re-enable it explicitly with torch.enable_grad()."""
+    import torch
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)

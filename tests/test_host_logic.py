@@ -49,13 +49,17 @@ def test_library_is_sm100a_and_has_no_other_arch(nat):
 def test_ctypes_structs_match_c_layout(nat, tmp_path):
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "egnn_b200.h"\nint main(){\n'
-                    'printf("%zu %zu %zu\\n", sizeof(EgnnLayerDesc), sizeof(EgnnLayerWeights), sizeof(EgnnLayerIO));\n'
+                    'printf("%zu %zu %zu %zu %zu\\n", sizeof(EgnnLayerDesc), sizeof(EgnnLayerWeights), sizeof(EgnnLayerIO),'
+                    ' sizeof(EgnnLayerWeightGrads), sizeof(EgnnLayerGrads));\n'
                     'printf("%zu %zu %zu %zu\\n", offsetof(EgnnLayerDesc, flags), offsetof(EgnnLayerDesc, valid_radius),'
-                    ' offsetof(EgnnLayerDesc, row_end), offsetof(EgnnLayerIO, feats_out));\nreturn 0;}\n')
+                    ' offsetof(EgnnLayerDesc, row_end), offsetof(EgnnLayerIO, feats_out));\n'
+                    'printf("%zu %zu\\n", offsetof(EgnnLayerGrads, g_edges), offsetof(EgnnLayerGrads, w));\nreturn 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), str(prog), "-o", str(exe)], check=True)
-    a, b = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
-    assert [int(x) for x in a.split()] == [C.sizeof(nat.LayerDesc), C.sizeof(nat.LayerWeights), C.sizeof(nat.LayerIO)]
+    a, b, c = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    assert [int(x) for x in a.split()] == [C.sizeof(nat.LayerDesc), C.sizeof(nat.LayerWeights), C.sizeof(nat.LayerIO),
+                                           C.sizeof(nat.LayerWeightGrads), C.sizeof(nat.LayerGrads)]
+    assert [int(x) for x in c.split()] == [nat.LayerGrads.g_edges.offset, nat.LayerGrads.w.offset]
     assert [int(x) for x in b.split()] == [nat.LayerDesc.flags.offset, nat.LayerDesc.valid_radius.offset,
                                            nat.LayerDesc.row_end.offset, nat.LayerIO.feats_out.offset]
 
@@ -71,6 +75,9 @@ def test_host_side_validation_without_gpu(nat):
     assert lib.egnn_layer_workspace_bytes(C.byref(d), C.byref(nb)) == 0
     E = 2 * 32 + 1
     assert nb.value >= 2 * 16 * 2 * (2 * E) * 4          # the two per-node tables
+    assert lib.egnn_layer_backward_workspace_bytes(C.byref(d), C.byref(nb)) == 0 and nb.value > 2 * 16 * 16 * 20 * 4
+    for unsupported in (dict(dtype=nat.DTYPE_BF16), dict(row_begin=0, row_end=8), dict(label_dim=4, num_labels=40)):
+        assert lib.egnn_layer_backward_workspace_bytes(C.byref(nat.LayerDesc(**dict(good, **unsupported))), C.byref(nb)) == -3
     for bad, code in [(dict(abi_version=7), -6), (dict(N=0), -2), (dict(C=9), -3), (dict(m_dim=64), -3),
                       (dict(k=17), -2), (dict(flags=0), -2), (dict(dtype=9), -3), (dict(row_begin=5, row_end=3), -2)]:
         d = nat.LayerDesc(**dict(good, **bad))

@@ -7,6 +7,8 @@ import sys
 
 import torch
 
+torch.set_grad_enabled(False)      # forward benchmark: no autograd state is kept
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [REPO]
 from egnn_pytorch_b200 import EGNN, _native as nat  # noqa: E402
