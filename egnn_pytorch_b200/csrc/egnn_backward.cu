@@ -76,10 +76,22 @@ static int launch_pair_bwd(BwdArgs<T>& a, cudaStream_t st) {
   dim3 g1(ceil_div(s.N, TI), s.B);
   pair_bwd1_kernel<T, MP, KNN><<<g1, PAIR_THREADS, smem1, st>>>(a);
   EGNN_LAUNCH_CHECK();
-  const size_t smem2 = bwd2_smem_bytes<T>(s, MP, a.TI2);
-  EGNN_TRY(opt_in_smem(pair_bwd2_kernel<T, MP, KNN>, smem2));
-  dim3 g2(ceil_div(s.N, a.TI2), ceil_div(s.Hp, BW2_TH), s.B);
-  pair_bwd2_kernel<T, MP, KNN><<<g2, BW2_TH, smem2, st>>>(a);
+  if constexpr (KNN) {
+    const size_t smem2 = bwd2_smem_bytes<T>(s, MP, a.TI2);
+    EGNN_TRY(opt_in_smem(pair_bwd2_kernel<T, MP, KNN>, smem2));
+    dim3 g2(ceil_div(s.N, a.TI2), ceil_div(s.Hp, BW2_TH), s.B);
+    pair_bwd2_kernel<T, MP, KNN><<<g2, BW2_TH, smem2, st>>>(a);
+  } else {
+    const size_t smem2 = bwd2_dense_smem_bytes<T>(s, a.rl.R);
+    dim3 g2(ceil_div(s.N, BW2_ROWS), ceil_div(s.Hp, BW2_TH), s.B);
+    if (s.Q == 1 && s.label_dim == 0) {
+      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, true>, smem2));
+      pair_bwd2_dense_kernel<T, MP, true><<<g2, BW2_TH, smem2, st>>>(a);
+    } else {
+      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, false>, smem2));
+      pair_bwd2_dense_kernel<T, MP, false><<<g2, BW2_TH, smem2, st>>>(a);
+    }
+  }
   EGNN_LAUNCH_CHECK();
   pair_bwd3_kernel<T, KNN><<<g1, PAIR_THREADS, 0, st>>>(a);
   EGNN_LAUNCH_CHECK();

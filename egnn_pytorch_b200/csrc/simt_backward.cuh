@@ -67,6 +67,22 @@ struct BwdArgs {
 
 template <typename T> __device__ __forceinline__ T dsilu_from(T x, T sg) { return sg * (T(1) + x * (T(1) - sg)); }
 
+// Record index of pair (b, i, slot).  kNN: row-major (b, i, slot).  Dense: (b, j, i) -- "column-major" -- so that the
+// records of 32 consecutive rows i for one neighbour j are contiguous, which is what a bwd2 CTA streams.
+template <bool KNN>
+__device__ __forceinline__ size_t rec_index(int b, int N, int J, int i, int slot) {
+  return KNN ? ((size_t)b * N + i) * J + slot : ((size_t)b * N + slot) * N + i;
+}
+
+__device__ __forceinline__ void cp_async_elem(void* smem_dst, const float* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(void* smem_dst, const double* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // =====================================================================================
 // bwd1
 // =====================================================================================
@@ -405,7 +421,7 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
       gmm[o] = gp2;                                   // reuse as the value written to the record
     }
     if (pair_exists) {
-      T* r = a.rec + (node_i * (size_t)J + sidx) * a.rl.R;
+      T* r = a.rec + rec_index<KNN>(b, s.N, J, i, sidx) * a.rl.R;
 #pragma unroll
       for (int o = 0; o < MP; ++o) r[a.rl.gpre2 + o] = gmm[o];
       if (s.Q > 1) {
@@ -572,7 +588,7 @@ pair_bwd2_kernel(const BwdArgs<T> a) {
       const int p = x / (MP + s.Q), e = x % (MP + s.Q);
       T v = T(0);
       if (hdr[p * 4 + 1] >= 0) {
-        const size_t pair = ((size_t)b * s.N + i0 + hdr[p * 4 + 0]) * J + hdr[p * 4 + 3];
+        const size_t pair = rec_index<KNN>(b, s.N, J, i0 + hdr[p * 4 + 0], hdr[p * 4 + 3]);
         v = a.rec[pair * a.rl.R + e];                      // g_pre2 and f are the first MP + Q entries
       }
       recs[p * RS + e] = v;
@@ -622,7 +638,7 @@ pair_bwd2_kernel(const BwdArgs<T> a) {
     for (int x = tid; x < BW2_PB * s.Q; x += BW2_TH) {
       const int p = x / s.Q, q = x % s.Q;
       if (hdr[p * 4 + 1] >= 0) {
-        const size_t pair = ((size_t)b * s.N + i0 + hdr[p * 4 + 0]) * J + hdr[p * 4 + 3];
+        const size_t pair = rec_index<KNN>(b, s.N, J, i0 + hdr[p * 4 + 0], hdr[p * 4 + 3]);
         atomic_add_t<T>(a.rec + pair * a.rl.R + a.rl.gf + q, gfs[x]);
       }
       gfs[x] = T(0);
@@ -635,6 +651,170 @@ pair_bwd2_kernel(const BwdArgs<T> a) {
     for (int o = 0; o < MP; ++o) atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2[o]);
     for (int q = 0; q < s.Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
     for (int l = 0; l < NL; ++l) atomic_add_t<T>(a.gpk + a.L.tab + (size_t)l * s.Hp + hh, gtabs[l * BW2_TH + tid]);
+  }
+}
+
+
+// =====================================================================================
+// bwd2, dense all-pairs specialisation: CTA = 32 rows x 128 channels, one neighbour j per step.  The 32 records of
+// (i0..i0+31, j) are contiguous (rec_index<false>) and are prefetched one step ahead with cp.async; row sums dL/dA live
+// in registers (the pair loop is unrolled over the 32 rows), the column sum dL/dB_j is one atomic per step, and
+// dL/df_q is reduced over the 128 channels through a [32][128] shared tile instead of per-pair shuffles.
+// SIMPLE = only the distance channel (Q == 1) and no label table: the common EGNN(dim) configuration.
+// =====================================================================================
+constexpr int BW2_ROWS = 32;
+
+template <typename T>
+inline size_t bwd2_dense_smem_bytes(const Dims& s, int R) {
+  const int NL = s.label_dim > 0 ? s.num_labels : 0;
+  size_t n = 0;
+  n += (size_t)BW2_ROWS * BW2_TH;           // As
+  n += (size_t)2 * s.Q * BW2_TH;            // wqs, gwqs
+  n += (size_t)2 * NL * BW2_TH;             // tabs, gtabs
+  n += (size_t)2 * BW2_ROWS * R;            // recs (double buffered)
+  n += (size_t)BW2_ROWS * BW2_TH;           // gps
+  return round_up(n * sizeof(T), 16) + 2 * BW2_ROWS * sizeof(int) + 16;
+}
+
+template <typename T, int MP, bool SIMPLE>
+__global__ void __launch_bounds__(BW2_TH)
+pair_bwd2_dense_kernel(const BwdArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Dims& s = a.s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.x * BW2_ROWS;
+  const int h0 = blockIdx.y * BW2_TH;
+  const int hh = h0 + tid;
+  const bool hv = hh < s.Hp;
+  const int N = s.N, R = a.rl.R, Q = s.Q;
+  const int NL = s.label_dim > 0 ? s.num_labels : 0;
+  const int nrows = min(BW2_ROWS, N - i0);
+
+  T* As = reinterpret_cast<T*>(smem_raw);        // [32][128]
+  T* wqs = As + BW2_ROWS * BW2_TH;               // [Q][128]
+  T* gwqs = wqs + Q * BW2_TH;                    // [Q][128]
+  T* tabs = gwqs + Q * BW2_TH;                   // [NL][128]
+  T* gtabs = tabs + NL * BW2_TH;                 // [NL][128]
+  T* recs = gtabs + NL * BW2_TH;                 // [2][32][R]
+  T* gps = recs + 2 * BW2_ROWS * R;              // [32][128]
+  int* labs = reinterpret_cast<int*>(smem_raw + round_up((size_t)(2 * BW2_ROWS * BW2_TH + 2 * Q * BW2_TH + 2 * NL * BW2_TH +
+                                                                   2 * BW2_ROWS * R) * sizeof(T), 16));   // [2][32]
+
+  const T* pk = a.packed;
+  for (int r = 0; r < BW2_ROWS; ++r)
+    As[r * BW2_TH + tid] = (r < nrows && hv) ? a.P[((size_t)b * N + i0 + r) * a.ldP + hh] : T(0);
+  for (int q = 0; q < Q; ++q) {
+    wqs[q * BW2_TH + tid] = hv ? pk[a.L.wq + (size_t)q * s.Hp + hh] : T(0);
+    gwqs[q * BW2_TH + tid] = T(0);
+  }
+  for (int l = 0; l < NL; ++l) {
+    tabs[l * BW2_TH + tid] = hv ? pk[a.L.tab + (size_t)l * s.Hp + hh] : T(0);
+    gtabs[l * BW2_TH + tid] = T(0);
+  }
+  for (int x = tid; x < 2 * BW2_ROWS * R; x += BW2_TH) recs[x] = T(0);     // rows >= nrows stay zero
+  if (tid < 2 * BW2_ROWS) labs[tid] = 0;
+  T w2r[MP], gW2[MP], gA[BW2_ROWS];
+#pragma unroll
+  for (int o = 0; o < MP; ++o) {
+    w2r[o] = hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0);
+    gW2[o] = T(0);
+  }
+#pragma unroll
+  for (int p = 0; p < BW2_ROWS; ++p) gA[p] = T(0);
+  const T wq0 = hv ? pk[a.L.wq + (size_t)(2 * s.F) * s.Hp + hh] : T(0);   // SIMPLE: the distance column
+  T gwq0 = T(0);
+  __syncthreads();
+
+  auto prefetch = [&](int j, int buf) {
+    const T* src = a.rec + rec_index<false>(b, N, N, i0, j) * R;
+    T* dst = recs + buf * BW2_ROWS * R;
+    for (int x = tid; x < nrows * R; x += BW2_TH) cp_async_elem(dst + x, src + x);
+    if (!SIMPLE && NL && tid < nrows) labs[buf * BW2_ROWS + tid] = a.labels[((size_t)b * N + i0 + tid) * N + j];
+    cp_async_commit_group();
+  };
+  prefetch(0, 0);
+  T bj_next = hv ? a.P[((size_t)b * N) * a.ldP + s.Hp + hh] : T(0);
+  cp_async_wait_all();
+  __syncthreads();
+
+  for (int j = 0; j < N; ++j) {
+    const int cur = j & 1;
+    if (j + 1 < N) prefetch(j + 1, cur ^ 1);
+    const T bj = bj_next;
+    if (j + 1 < N) bj_next = hv ? a.P[((size_t)b * N + j + 1) * a.ldP + s.Hp + hh] : T(0);
+    const T* rb = recs + cur * BW2_ROWS * R;
+    T gB = T(0);
+#pragma unroll
+    for (int p = 0; p < BW2_ROWS; ++p) {
+      const T* r = rb + p * R;
+      T pre = As[p * BW2_TH + tid] + bj;
+      int lab = 0;
+      if (SIMPLE) {
+        pre = fma_t(wq0, r[MP], pre);
+      } else {
+        for (int q = 0; q < Q; ++q) pre = fma_t(wqs[q * BW2_TH + tid], r[MP + q], pre);
+        if (NL) { lab = labs[cur * BW2_ROWS + p]; pre += tabs[lab * BW2_TH + tid]; }
+      }
+      const T sg = sigmoid_acc<T>(pre);
+      const T a1 = pre * sg;
+      T ga1 = T(0);
+#pragma unroll
+      for (int o = 0; o < MP; o += 4) {
+        Vec4<T> gv;
+        gv.load(r + o);
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+          ga1 = fma_t(w2r[o + z], gv.v[z], ga1);
+          gW2[o + z] = fma_t(a1, gv.v[z], gW2[o + z]);
+        }
+      }
+      const T gp = ga1 * dsilu_from<T>(pre, sg);
+      gA[p] += gp;
+      gB += gp;
+      gps[p * BW2_TH + tid] = gp;
+      if (SIMPLE) {
+        gwq0 = fma_t(r[MP], gp, gwq0);
+      } else {
+        for (int q = 0; q < Q; ++q) gwqs[q * BW2_TH + tid] = fma_t(r[MP + q], gp, gwqs[q * BW2_TH + tid]);
+        if (NL) gtabs[lab * BW2_TH + tid] += gp;
+      }
+    }
+    if (hv) atomic_add_t<T>(a.gP + ((size_t)b * N + j) * a.ldP + s.Hp + hh, gB);
+    __syncthreads();                                   // gps complete
+    {
+      // dL/df_q(i0+p, j) = sum_h Wq[q][h] gp[p][h]: thread = (row p, quarter of the channels); lanes start at
+      // rotated offsets so that the 32 lanes of a warp hit 32 different banks
+      const int p = tid >> 2, qt = tid & 3;
+      const T* grow = gps + p * BW2_TH + qt * 32;
+      for (int q = 0; q < Q; ++q) {
+        const T* wrow = wqs + q * BW2_TH + qt * 32;
+        T v = T(0);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+          const int kk = (k + lane) & 31;
+          v = fma_t(wrow[kk], grow[kk], v);
+        }
+        v += shfl_xor_t<T>(v, 1);
+        v += shfl_xor_t<T>(v, 2);
+        if (qt == 0 && p < nrows) atomic_add_t<T>(a.rec + rec_index<false>(b, N, N, i0 + p, j) * R + a.rl.gf + q, v);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();                                   // next records landed; gps free
+  }
+  if (hv) {
+#pragma unroll
+    for (int p = 0; p < BW2_ROWS; ++p)
+      if (p < nrows) a.gP[((size_t)b * N + i0 + p) * a.ldP + hh] = gA[p];
+#pragma unroll
+    for (int o = 0; o < MP; ++o) atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2[o]);
+    if (SIMPLE) {
+      atomic_add_t<T>(a.gpk + a.L.wq + (size_t)(2 * s.F) * s.Hp + hh, gwq0);
+    } else {
+      for (int q = 0; q < Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
+      for (int l = 0; l < NL; ++l) atomic_add_t<T>(a.gpk + a.L.tab + (size_t)l * s.Hp + hh, gtabs[l * BW2_TH + tid]);
+    }
   }
 }
 
@@ -667,7 +847,7 @@ pair_bwd3_kernel(const BwdArgs<T> a) {
     if (!(row_valid && sidx < J)) continue;
     int j = KNN ? a.nbr_idx[node_i * s.k + sidx] : sidx;
     if (j < 0) continue;
-    const T* r = a.rec + (node_i * (size_t)J + sidx) * a.rl.R;
+    const T* r = a.rec + rec_index<KNN>(b, s.N, J, i, sidx) * a.rl.R;
     const T* xj = a.coors + ((size_t)b * s.N + j) * s.C;
     T rel[PAIR_CMAX];
     T d = T(0);
