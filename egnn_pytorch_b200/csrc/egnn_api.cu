@@ -16,14 +16,7 @@ int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* c
 template <typename T, int MP, bool KNN>
 static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
   const size_t smem = pair_smem_bytes<T>(a.s, a.L, KNN);
-  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
-  static size_t smem_set[64] = {0};                 // per device: largest dynamic-smem size already opted in
-  int dev = 0;
-  EGNN_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 64 && smem_set[dev] < smem) {
-    EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_kernel<T, MP, KNN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[dev] = smem;
-  }
+  EGNN_TRY(ensure_dynamic_smem(pair_kernel<T, MP, KNN>, smem));
   const int TI = PAIR_THREADS / a.TS;
   dim3 grid(ceil_div(a.s.row1 - a.s.row0, TI), a.s.B);
   pair_kernel<T, MP, KNN><<<grid, PAIR_THREADS, smem, st>>>(a);
@@ -35,14 +28,7 @@ static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
 template <typename T, int MP, int PP>
 static int launch_pair_tiled(const PairArgs<T>& a, cudaStream_t st) {
   const size_t smem = pair_tiled_smem_bytes<T>(a.s, a.L, PP);
-  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
-  static size_t smem_set[64] = {0};
-  int dev = 0;
-  EGNN_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 64 && smem_set[dev] < smem) {
-    EGNN_CUDA_TRY(cudaFuncSetAttribute(pair_dense_tiled_kernel<T, MP, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set[dev] = smem;
-  }
+  EGNN_TRY(ensure_dynamic_smem(pair_dense_tiled_kernel<T, MP, PP>, smem));
   dim3 grid(ceil_div(a.s.row1 - a.s.row0, 4 * PP), a.s.B);
   if (a.hsplit > 1) {
     PairArgs<T> a1 = a, a2 = a;

@@ -8,7 +8,7 @@
 namespace egnn {
 
 struct BwdWs {
-  size_t gP, gpk, rec, h1pre, ga, g_node_in, gyx, total;
+  size_t gP, gpk, rec, pre2, h1pre, ga, g_node_in, gyx, total;
 };
 
 static BwdWs bwd_ws_layout(const Dims& s, const SimtPackLayout& L, size_t es, uint32_t flags) {
@@ -20,6 +20,7 @@ static BwdWs bwd_ws_layout(const Dims& s, const SimtPackLayout& L, size_t es, ui
   w.gP = take((size_t)s.M * 2 * s.Hp * es);
   w.gpk = take(L.total * es);
   w.rec = take((size_t)s.M * J * rec_layout(s, L.MP).R * es);
+  w.pre2 = take(s.k == 0 ? (size_t)s.M * s.N * L.MP * es : 0);
   w.h1pre = take(uf ? (size_t)s.M * 2 * s.dim * es : 0);
   w.ga = take(uf ? (size_t)s.M * 2 * s.dim * es : 0);
   w.g_node_in = take(uf ? (size_t)s.M * (s.dim + s.m) * es : 0);
@@ -61,15 +62,35 @@ static int launch_colsum(const T* X, long ld, int rows, int cols, T* out, cudaSt
 }
 
 template <typename K>
-static int opt_in_smem(K kernel, size_t smem) {
-  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024) EGNN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+static int opt_in_smem(K kernel, size_t smem) { return ensure_dynamic_smem(kernel, smem); }
+
+// Dense: W2 silu(pre1) for every pair with the register-tiled forward kernel (its split-H "phase 1" stores exactly
+// that); returns EGNN_ERR_UNSUPPORTED when its shared memory does not fit, and bwd1 then recomputes by itself.
+template <typename T, int MP, int PP>
+static int launch_tiled_recompute(const BwdArgs<T>& a, T* pre2, cudaStream_t st) {
+  PairArgs<T> f;
+  f.s = a.s; f.L = a.L; f.flags = a.flags; f.has_mask = a.has_mask; f.TS = 32; f.clamp = a.clamp;
+  f.P = a.P; f.ldP = a.ldP; f.coors = a.coors; f.edges = a.edges; f.labels = a.labels; f.mask = a.mask;
+  f.nbr_idx = nullptr; f.nbr_ok = nullptr; f.packed = a.packed;
+  f.m_out = nullptr; f.ld_m = 0; f.coors_out = nullptr;
+  f.hpart = pre2; f.hsplit = 1; f.phase = 1;
+  const size_t smem = pair_tiled_smem_bytes<T>(a.s, a.L, PP);
+  EGNN_TRY(opt_in_smem(pair_dense_tiled_kernel<T, MP, PP>, smem));
+  dim3 grid(ceil_div(a.s.N, 4 * PP), a.s.B, 1);
+  pair_dense_tiled_kernel<T, MP, PP><<<grid, PAIR_THREADS, smem, st>>>(f);
+  EGNN_LAUNCH_CHECK();
   return EGNN_OK;
 }
 
 template <typename T, int MP, bool KNN>
 static int launch_pair_bwd(BwdArgs<T>& a, cudaStream_t st) {
   const Dims& s = a.s;
+  if constexpr (!KNN) {
+    T* pre2 = const_cast<T*>(a.pre2);
+    const int rc = launch_tiled_recompute<T, MP, (MP == 32 && sizeof(T) == 8) ? 1 : 2>(a, pre2, st);
+    if (rc == EGNN_ERR_UNSUPPORTED) a.pre2 = nullptr;
+    else EGNN_TRY(rc);
+  }
   const size_t smem1 = bwd1_smem_bytes<T>(s, a.L, KNN, (a.flags & EGNN_FLAG_SOFT_EDGES) != 0);
   EGNN_TRY(opt_in_smem(pair_bwd1_kernel<T, MP, KNN>, smem1));
   const int TI = PAIR_THREADS / a.TS;
@@ -204,6 +225,7 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
   a.packed = static_cast<const T*>(packed);
   a.g_node_in = uf ? g_node_in : nullptr; a.ld_g = dn;
   a.g_coors_out = static_cast<const T*>(gr.g_coors_out);
+  a.pre2 = s.k == 0 ? reinterpret_cast<const T*>(base + bl.pre2) : nullptr;
   a.rec = rec; a.gpk = gpk; a.gP = gP; a.g_coors = g_coors;
   a.g_edges = (s.edge_dim > 0) ? static_cast<T*>(gr.g_edges) : nullptr;
   if (s.k > 0) {

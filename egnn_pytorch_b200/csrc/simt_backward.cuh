@@ -58,6 +58,8 @@ struct BwdArgs {
   const T* packed;
   const T* g_node_in; int ld_g;   // [M][dim+m]; dL/dm_i = columns dim..dim+m  (null when !update_feats)
   const T* g_coors_out;           // [B,N,C]
+  const T* pre2;                  // dense only, optional: W2 silu(pre1) per pair, row-major [B,N,N][MP], recomputed by the
+                                  // register-tiled forward kernel; null = bwd1 recomputes it itself
   T* rec;                         // [pairs][R]
   T* gpk;                         // gradient accumulators in SimtPackLayout order (zeroed by the caller)
   T* gP;                          // [M][2*Hp]: dL/dA | dL/dB (zeroed by the caller)
@@ -239,8 +241,21 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
 #pragma unroll
     for (int o = 0; o < MP; ++o) acc[o] = T(0);
 
-    // ---- forward recompute of W2 silu(pre1) (identical to pair_kernel)
-    for (int c0 = 0; c0 < s.Hp; c0 += PAIR_CH) {
+    // ---- forward recompute of W2 silu(pre1) (identical to pair_kernel), unless the caller already did it
+    if (a.pre2) {
+      __syncthreads();                               // tiles of the previous iteration fully consumed
+      if (pair_exists) {
+        const T* src = a.pre2 + (node_i * s.N + sidx) * MP;
+#pragma unroll
+        for (int o = 0; o < MP; o += 4) {
+          Vec4<T> v;
+          v.load_g(src + o);
+#pragma unroll
+          for (int z = 0; z < 4; ++z) acc[o + z] = v.v[z];
+        }
+      }
+    }
+    for (int c0 = 0; c0 < (a.pre2 ? 0 : s.Hp); c0 += PAIR_CH) {
       const int cn = min(PAIR_CH, s.Hp - c0);
       __syncthreads();
       for (int x = tid; x < cn * MP; x += PAIR_THREADS) W2s[x] = pk[a.L.w2t + (size_t)c0 * MP + x];

@@ -58,6 +58,19 @@ static SimtWs simt_ws_layout(const Dims& s, size_t es, uint32_t flags) {
   return w;
 }
 
+// Opt a kernel in to `smem` bytes of dynamic shared memory.  The attribute is read back first and only ever raised:
+// the same kernel template is launched from several translation units, so no TU-local cache may lower it.
+template <typename K>
+static int ensure_dynamic_smem(K kernel, size_t smem) {
+  if (smem > 220 * 1024) return EGNN_ERR_UNSUPPORTED;
+  if (smem <= 48 * 1024) return EGNN_OK;
+  cudaFuncAttributes attr;
+  EGNN_CUDA_TRY(cudaFuncGetAttributes(&attr, kernel));
+  if ((size_t)attr.maxDynamicSharedSizeBytes < smem)
+    EGNN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return EGNN_OK;
+}
+
 template <typename T, int ACT, bool RES>
 static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, const T* R, int ldr, T* C,
                        int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st) {
