@@ -98,19 +98,27 @@ static int launch_pair_bwd(BwdArgs<T>& a, cudaStream_t st) {
   pair_bwd1_kernel<T, MP, KNN><<<g1, PAIR_THREADS, smem1, st>>>(a);
   EGNN_LAUNCH_CHECK();
   if constexpr (KNN) {
-    const size_t smem2 = bwd2_smem_bytes<T>(s, MP, a.TI2);
-    EGNN_TRY(opt_in_smem(pair_bwd2_kernel<T, MP, KNN>, smem2));
+    const size_t smem2 = bwd2_knn_smem_bytes<T>(s, a.rl.R);
     dim3 g2(ceil_div(s.N, a.TI2), ceil_div(s.Hp, BW2_TH), s.B);
-    pair_bwd2_kernel<T, MP, KNN><<<g2, BW2_TH, smem2, st>>>(a);
+    if (s.Q == 1 && s.label_dim == 0) {
+      EGNN_TRY(opt_in_smem(pair_bwd2_knn_kernel<T, MP, 1>, smem2));
+      pair_bwd2_knn_kernel<T, MP, 1><<<g2, BW2_TH, smem2, st>>>(a);
+    } else if (s.Q <= 8) {
+      EGNN_TRY(opt_in_smem(pair_bwd2_knn_kernel<T, MP, 8>, smem2));
+      pair_bwd2_knn_kernel<T, MP, 8><<<g2, BW2_TH, smem2, st>>>(a);
+    } else {
+      EGNN_TRY(opt_in_smem(pair_bwd2_knn_kernel<T, MP, 0>, smem2));
+      pair_bwd2_knn_kernel<T, MP, 0><<<g2, BW2_TH, smem2, st>>>(a);
+    }
   } else {
     const size_t smem2 = bwd2_dense_smem_bytes<T>(s, a.rl.R);
     dim3 g2(ceil_div(s.N, BW2_ROWS), ceil_div(s.Hp, BW2_TH), s.B);
     if (s.Q == 1 && s.label_dim == 0) {
-      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, true>, smem2));
-      pair_bwd2_dense_kernel<T, MP, true><<<g2, BW2_TH, smem2, st>>>(a);
+      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, 1>, smem2));
+      pair_bwd2_dense_kernel<T, MP, 1><<<g2, BW2_TH, smem2, st>>>(a);
     } else {
-      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, false>, smem2));
-      pair_bwd2_dense_kernel<T, MP, false><<<g2, BW2_TH, smem2, st>>>(a);
+      EGNN_TRY(opt_in_smem(pair_bwd2_dense_kernel<T, MP, 0>, smem2));
+      pair_bwd2_dense_kernel<T, MP, 0><<<g2, BW2_TH, smem2, st>>>(a);
     }
   }
   EGNN_LAUNCH_CHECK();
@@ -231,7 +239,7 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
   if (s.k > 0) {
     int TS = 1;
     while (TS < s.k && TS < 32) TS <<= 1;
-    a.TS = TS; a.TI2 = 8;
+    a.TS = TS; a.TI2 = 16;
     if (L.MP == 16) EGNN_TRY((launch_pair_bwd<T, 16, true>(a, st)));
     else EGNN_TRY((launch_pair_bwd<T, 32, true>(a, st)));
   } else {

@@ -505,62 +505,56 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
 }
 
 // =====================================================================================
-// bwd2: thread = hidden channel; CTA = TI2 rows x 128 channels; pairs streamed in batches of 32.
+// bwd2, neighbour-list form: thread = hidden channel, CTA = TI2 rows x 128 channels.  One step = up to 32 slots of
+// one row: their records are contiguous (rec_index<true>) and are prefetched one step ahead with cp.async together
+// with the neighbour indices; the 32 gathered B rows are loaded up front (32 independent L2 requests per thread),
+// dL/dA_i is a register, dL/dB_j one fire-and-forget atomic per (pair, channel) -- the scatter is inherent to a
+// neighbour list -- and dL/df_q is reduced over the channels through a [32][128] shared tile.
 // =====================================================================================
 constexpr int BW2_TH = 128;       // channels per CTA
-constexpr int BW2_PB = 32;        // pairs per staged batch
+constexpr int BW2_PB = 32;        // pairs per step
 constexpr int BW2_MAXLAB = 16;    // label rows kept in shared memory
 
 template <typename T>
-inline size_t bwd2_smem_bytes(const Dims& s, int MP, int TI2) {
+inline size_t bwd2_knn_smem_bytes(const Dims& s, int R) {
   const int NL = s.label_dim > 0 ? s.num_labels : 0;
-  const int RS = round_up_i(MP + s.Q, 4);
   size_t n = 0;
-  n += (size_t)2 * TI2 * BW2_TH;            // As, gAs
   n += (size_t)2 * s.Q * BW2_TH;            // wqs, gwqs
   n += (size_t)2 * NL * BW2_TH;             // tabs, gtabs
-  n += (size_t)BW2_PB * RS;                 // recs
-  n += (size_t)BW2_PB * s.Q;                // gfs
-  return round_up(n * sizeof(T), 16) + BW2_PB * 4 * sizeof(int) + 16;
+  n += (size_t)2 * BW2_PB * R;              // recs (double buffered)
+  n += (size_t)BW2_PB * BW2_TH;             // gps
+  return round_up(n * sizeof(T), 16) + 4 * BW2_PB * sizeof(int) + 16;
 }
 
-template <typename T, int MP, bool KNN>
+template <typename T, int MP, int QR>
 __global__ void __launch_bounds__(BW2_TH)
-pair_bwd2_kernel(const BwdArgs<T> a) {
+pair_bwd2_knn_kernel(const BwdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Dims& s = a.s;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int TI2 = a.TI2;
   const int b = blockIdx.z;
-  const int i0 = blockIdx.x * TI2;
+  const int i0 = blockIdx.x * a.TI2;
   const int h0 = blockIdx.y * BW2_TH;
   const int hh = h0 + tid;
   const bool hv = hh < s.Hp;
-  const int J = KNN ? s.k : s.N;
+  const int N = s.N, R = a.rl.R, Q = s.Q, k = s.k;
   const int NL = s.label_dim > 0 ? s.num_labels : 0;
-  const int RS = round_up_i(MP + s.Q, 4);
-  const int nrows = min(TI2, s.N - i0);
+  const int nrows = min(a.TI2, N - i0);
+  const int nch = ceil_div(k, BW2_PB);
+  const int nsteps = nrows * nch;
 
-  T* As = reinterpret_cast<T*>(smem_raw);       // [TI2][128]
-  T* gAs = As + TI2 * BW2_TH;                   // [TI2][128]
-  T* wqs = gAs + TI2 * BW2_TH;                  // [Q][128]
-  T* gwqs = wqs + s.Q * BW2_TH;                 // [Q][128]
-  T* tabs = gwqs + s.Q * BW2_TH;                // [NL][128]
-  T* gtabs = tabs + NL * BW2_TH;                // [NL][128]
-  T* recs = gtabs + NL * BW2_TH;                // [PB][RS]: g_pre2[MP] | f[Q]
-  T* gfs = recs + BW2_PB * RS;                  // [PB][Q]
-  int* hdr = reinterpret_cast<int*>(smem_raw + round_up((size_t)(2 * TI2 * BW2_TH + 2 * s.Q * BW2_TH + 2 * NL * BW2_TH +
-                                                                  BW2_PB * RS + BW2_PB * s.Q) * sizeof(T), 16));
-  // hdr[p] = {il, j (or -1), label, unused}; the record index is recomputed from (il, slot)
+  T* wqs = reinterpret_cast<T*>(smem_raw);       // [Q][128]
+  T* gwqs = wqs + Q * BW2_TH;                    // [Q][128]
+  T* tabs = gwqs + Q * BW2_TH;                   // [NL][128]
+  T* gtabs = tabs + NL * BW2_TH;                 // [NL][128]
+  T* recs = gtabs + NL * BW2_TH;                 // [2][32][R]
+  T* gps = recs + 2 * BW2_PB * R;                // [32][128]
+  int* nb = reinterpret_cast<int*>(smem_raw + round_up((size_t)(2 * Q * BW2_TH + 2 * NL * BW2_TH + 2 * BW2_PB * R +
+                                                                 BW2_PB * BW2_TH) * sizeof(T), 16));      // [2][32] neighbour
+  int* lb = nb + 2 * BW2_PB;                                                                              // [2][32] label
 
   const T* pk = a.packed;
-  for (int r = 0; r < TI2; ++r) {
-    T v = T(0);
-    if (r < nrows && hv) v = a.P[((size_t)b * s.N + i0 + r) * a.ldP + hh];
-    As[r * BW2_TH + tid] = v;
-    gAs[r * BW2_TH + tid] = T(0);
-  }
-  for (int q = 0; q < s.Q; ++q) {
+  for (int q = 0; q < Q; ++q) {
     wqs[q * BW2_TH + tid] = hv ? pk[a.L.wq + (size_t)q * s.Hp + hh] : T(0);
     gwqs[q * BW2_TH + tid] = T(0);
   }
@@ -568,107 +562,155 @@ pair_bwd2_kernel(const BwdArgs<T> a) {
     tabs[l * BW2_TH + tid] = hv ? pk[a.L.tab + (size_t)l * s.Hp + hh] : T(0);
     gtabs[l * BW2_TH + tid] = T(0);
   }
-  for (int x = tid; x < BW2_PB * s.Q; x += BW2_TH) gfs[x] = T(0);
   T w2r[MP], gW2[MP];
 #pragma unroll
   for (int o = 0; o < MP; ++o) {
     w2r[o] = hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0);
     gW2[o] = T(0);
   }
-
-  const int total = TI2 * J;
-  int curj = -1;
-  T gBacc = T(0), bj = T(0);
-  for (int q0 = 0; q0 < total; q0 += BW2_PB) {
-    __syncthreads();                                     // previous batch consumed (and the constants staged)
-    if (tid < BW2_PB) {
-      const int seq = q0 + tid;
-      int il = 0, j = -1, lab = 0, slot = 0;
-      if (seq < total) {
-        if (KNN) { il = seq / J; slot = seq % J; }
-        else { slot = seq / TI2; il = seq % TI2; }
-        if (il < nrows) {
-          const size_t node = (size_t)b * s.N + i0 + il;
-          j = KNN ? a.nbr_idx[node * s.k + slot] : slot;
-          if (j >= 0 && a.labels) lab = a.labels[node * s.N + j];
-        }
-      }
-      hdr[tid * 4 + 0] = il;
-      hdr[tid * 4 + 1] = j;
-      hdr[tid * 4 + 2] = lab;
-      hdr[tid * 4 + 3] = slot;
-    }
-    __syncthreads();
-    for (int x = tid; x < BW2_PB * (MP + s.Q); x += BW2_TH) {
-      const int p = x / (MP + s.Q), e = x % (MP + s.Q);
-      T v = T(0);
-      if (hdr[p * 4 + 1] >= 0) {
-        const size_t pair = rec_index<KNN>(b, s.N, J, i0 + hdr[p * 4 + 0], hdr[p * 4 + 3]);
-        v = a.rec[pair * a.rl.R + e];                      // g_pre2 and f are the first MP + Q entries
-      }
-      recs[p * RS + e] = v;
-    }
-    __syncthreads();
-
-    for (int p = 0; p < BW2_PB; ++p) {
-      const int j = hdr[p * 4 + 1];
-      if (j < 0) continue;                               // uniform over the CTA
-      const int il = hdr[p * 4 + 0], lab = hdr[p * 4 + 2];
-      if (j != curj) {
-        if (curj >= 0 && hv) atomic_add_t<T>(a.gP + ((size_t)b * s.N + curj) * a.ldP + s.Hp + hh, gBacc);
-        gBacc = T(0);
-        curj = j;
-        bj = hv ? a.P[((size_t)b * s.N + j) * a.ldP + s.Hp + hh] : T(0);
-      }
-      const T* r = recs + p * RS;
-      T pre = As[il * BW2_TH + tid] + bj;
-      for (int q = 0; q < s.Q; ++q) pre = fma_t(wqs[q * BW2_TH + tid], r[MP + q], pre);
-      if (NL) pre += tabs[lab * BW2_TH + tid];
-      const T sg = sigmoid_acc<T>(pre);
-      const T a1 = pre * sg;
-      T ga1 = T(0);
+  const T wq0 = hv ? pk[a.L.wq + (size_t)(2 * s.F) * s.Hp + hh] : T(0);
+  T gwq0 = T(0);
+  constexpr bool SIMPLE = QR == 1;          // distance channel only, no label table
+  constexpr bool QREG = QR > 1;             // Q <= QR: per-pair scalar channels and their weights live in registers
+  constexpr int QN = QREG ? QR : 1;
+  T wqr[QN], gwqr[QN];
 #pragma unroll
-      for (int o = 0; o < MP; o += 4) {
-        Vec4<T> gv;
-        gv.load(r + o);
-#pragma unroll
-        for (int z = 0; z < 4; ++z) {
-          ga1 = fma_t(w2r[o + z], gv.v[z], ga1);
-          gW2[o + z] = fma_t(a1, gv.v[z], gW2[o + z]);
-        }
-      }
-      const T gp = ga1 * dsilu_from<T>(pre, sg);
-      gAs[il * BW2_TH + tid] += gp;
-      gBacc += gp;
-      if (NL) gtabs[lab * BW2_TH + tid] += gp;
-      for (int q = 0; q < s.Q; ++q) {
-        gwqs[q * BW2_TH + tid] = fma_t(r[MP + q], gp, gwqs[q * BW2_TH + tid]);
-        T part = wqs[q * BW2_TH + tid] * gp;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) part += shfl_xor_t<T>(part, off);
-        if (lane == 0) atomic_add_t<T>(gfs + p * s.Q + q, part);
-      }
-    }
-    __syncthreads();
-    for (int x = tid; x < BW2_PB * s.Q; x += BW2_TH) {
-      const int p = x / s.Q, q = x % s.Q;
-      if (hdr[p * 4 + 1] >= 0) {
-        const size_t pair = rec_index<KNN>(b, s.N, J, i0 + hdr[p * 4 + 0], hdr[p * 4 + 3]);
-        atomic_add_t<T>(a.rec + pair * a.rl.R + a.rl.gf + q, gfs[x]);
-      }
-      gfs[x] = T(0);
-    }
+  for (int q = 0; q < QN; ++q) {
+    wqr[q] = (QREG && q < Q && hv) ? pk[a.L.wq + (size_t)q * s.Hp + hh] : T(0);
+    gwqr[q] = T(0);
   }
-  if (curj >= 0 && hv) atomic_add_t<T>(a.gP + ((size_t)b * s.N + curj) * a.ldP + s.Hp + hh, gBacc);
+
+  auto prefetch = [&](int t, int buf) {
+    const int row = t / nch, c0 = (t % nch) * BW2_PB, kc = min(BW2_PB, k - c0);
+    const size_t node = (size_t)b * N + i0 + row;
+    const T* src = a.rec + rec_index<true>(b, N, k, i0 + row, c0) * R;
+    T* dst = recs + buf * BW2_PB * R;
+    for (int x = tid; x < kc * R; x += BW2_TH) cp_async_elem(dst + x, src + x);
+    if (tid < BW2_PB) {
+      const int j = tid < kc ? a.nbr_idx[node * k + c0 + tid] : -1;
+      nb[buf * BW2_PB + tid] = j;
+      lb[buf * BW2_PB + tid] = (NL && j >= 0) ? a.labels[node * N + j] : 0;
+    }
+    cp_async_commit_group();
+  };
+  if (nsteps > 0) prefetch(0, 0);
+  cp_async_wait_all();
+  __syncthreads();
+
+  int cur_row = -1;
+  T Ai = T(0), gA = T(0);
+  for (int t = 0; t < nsteps; ++t) {
+    const int cur = t & 1;
+    const int row = t / nch, c0 = (t % nch) * BW2_PB, kc = min(BW2_PB, k - c0);
+    if (t + 1 < nsteps) prefetch(t + 1, cur ^ 1);
+    if (row != cur_row) {
+      if (cur_row >= 0 && hv) a.gP[((size_t)b * N + i0 + cur_row) * a.ldP + hh] = gA;
+      gA = T(0);
+      cur_row = row;
+      Ai = hv ? a.P[((size_t)b * N + i0 + row) * a.ldP + hh] : T(0);
+    }
+    const int* nbc = nb + cur * BW2_PB;
+    const T* rb = recs + cur * BW2_PB * R;
+    T bjv[BW2_PB];
+#pragma unroll
+    for (int p = 0; p < BW2_PB; ++p) {
+      const int j = nbc[p];
+      bjv[p] = (j >= 0 && hv) ? a.P[((size_t)b * N + j) * a.ldP + s.Hp + hh] : T(0);
+    }
+#pragma unroll
+    for (int p = 0; p < BW2_PB; ++p) {
+      if (p >= kc) break;                              // uniform
+      const int j = nbc[p];
+      T gp = T(0);
+      if (j >= 0) {                                    // uniform
+        const T* r = rb + p * R;
+        T pre = Ai + bjv[p];
+        int lab = 0;
+        T fq[QN];
+        if (SIMPLE) {
+          pre = fma_t(wq0, r[MP], pre);
+        } else {
+          if (QREG) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+              if (q < Q) { fq[q] = r[MP + q]; pre = fma_t(wqr[q], fq[q], pre); }
+          } else {
+            for (int q = 0; q < Q; ++q) pre = fma_t(wqs[q * BW2_TH + tid], r[MP + q], pre);
+          }
+          if (NL) { lab = lb[cur * BW2_PB + p]; pre += tabs[lab * BW2_TH + tid]; }
+        }
+        const T sg = sigmoid_acc<T>(pre);
+        const T a1 = pre * sg;
+        T ga1 = T(0);
+#pragma unroll
+        for (int o = 0; o < MP; o += 4) {
+          Vec4<T> gv;
+          gv.load(r + o);
+#pragma unroll
+          for (int z = 0; z < 4; ++z) {
+            ga1 = fma_t(w2r[o + z], gv.v[z], ga1);
+            gW2[o + z] = fma_t(a1, gv.v[z], gW2[o + z]);
+          }
+        }
+        gp = ga1 * dsilu_from<T>(pre, sg);
+        gA += gp;
+        if (hv) atomic_add_t<T>(a.gP + ((size_t)b * N + j) * a.ldP + s.Hp + hh, gp);
+        if (SIMPLE) {
+          gwq0 = fma_t(r[MP], gp, gwq0);
+        } else {
+          if (QREG) {
+#pragma unroll
+            for (int q = 0; q < QN; ++q)
+              if (q < Q) gwqr[q] = fma_t(fq[q], gp, gwqr[q]);
+          } else {
+            for (int q = 0; q < Q; ++q) gwqs[q * BW2_TH + tid] = fma_t(r[MP + q], gp, gwqs[q * BW2_TH + tid]);
+          }
+          if (NL) gtabs[lab * BW2_TH + tid] += gp;
+        }
+      }
+      gps[p * BW2_TH + tid] = gp;
+    }
+    __syncthreads();                                   // gps complete
+    {
+      const int p = tid >> 2, qt = tid & 3;
+      const bool live = p < kc && nbc[p] >= 0;
+      const T* grow = gps + p * BW2_TH + qt * 32;
+      for (int q = 0; q < Q; ++q) {
+        const T* wrow = wqs + q * BW2_TH + qt * 32;
+        T v = T(0);
+        if (live) {
+#pragma unroll 8
+          for (int kx = 0; kx < 32; ++kx) {
+            const int kk = (kx + lane) & 31;
+            v = fma_t(wrow[kk], grow[kk], v);
+          }
+        }
+        v += shfl_xor_t<T>(v, 1);
+        v += shfl_xor_t<T>(v, 2);
+        if (qt == 0 && live) atomic_add_t<T>(a.rec + rec_index<true>(b, N, k, i0 + row, c0 + p) * R + a.rl.gf + q, v);
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();                                   // next records landed; gps free
+  }
   if (hv) {
-    for (int r = 0; r < nrows; ++r) a.gP[((size_t)b * s.N + i0 + r) * a.ldP + hh] = gAs[r * BW2_TH + tid];
+    if (cur_row >= 0) a.gP[((size_t)b * N + i0 + cur_row) * a.ldP + hh] = gA;
 #pragma unroll
     for (int o = 0; o < MP; ++o) atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2[o]);
-    for (int q = 0; q < s.Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
-    for (int l = 0; l < NL; ++l) atomic_add_t<T>(a.gpk + a.L.tab + (size_t)l * s.Hp + hh, gtabs[l * BW2_TH + tid]);
+    if (SIMPLE) {
+      atomic_add_t<T>(a.gpk + a.L.wq + (size_t)(2 * s.F) * s.Hp + hh, gwq0);
+    } else {
+      if (QREG) {
+#pragma unroll
+        for (int q = 0; q < QN; ++q)
+          if (q < Q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqr[q]);
+      } else {
+        for (int q = 0; q < Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
+      }
+      for (int l = 0; l < NL; ++l) atomic_add_t<T>(a.gpk + a.L.tab + (size_t)l * s.Hp + hh, gtabs[l * BW2_TH + tid]);
+    }
   }
 }
-
 
 // =====================================================================================
 // bwd2, dense all-pairs specialisation: CTA = 32 rows x 128 channels, one neighbour j per step.  The 32 records of
@@ -691,7 +733,7 @@ inline size_t bwd2_dense_smem_bytes(const Dims& s, int R) {
   return round_up(n * sizeof(T), 16) + 2 * BW2_ROWS * sizeof(int) + 16;
 }
 
-template <typename T, int MP, bool SIMPLE>
+template <typename T, int MP, int QR>
 __global__ void __launch_bounds__(BW2_TH)
 pair_bwd2_dense_kernel(const BwdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -739,6 +781,15 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
   for (int p = 0; p < BW2_ROWS; ++p) gA[p] = T(0);
   const T wq0 = hv ? pk[a.L.wq + (size_t)(2 * s.F) * s.Hp + hh] : T(0);   // SIMPLE: the distance column
   T gwq0 = T(0);
+  constexpr bool SIMPLE = QR == 1;          // distance channel only, no label table
+  constexpr bool QREG = QR > 1;             // Q <= QR: per-pair scalar channels and their weights live in registers
+  constexpr int QN = QREG ? QR : 1;
+  T wqr[QN], gwqr[QN];
+#pragma unroll
+  for (int q = 0; q < QN; ++q) {
+    wqr[q] = (QREG && q < Q && hv) ? pk[a.L.wq + (size_t)q * s.Hp + hh] : T(0);
+    gwqr[q] = T(0);
+  }
   __syncthreads();
 
   auto prefetch = [&](int j, int buf) {
@@ -765,10 +816,17 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
       const T* r = rb + p * R;
       T pre = As[p * BW2_TH + tid] + bj;
       int lab = 0;
+      T fq[QN];
       if (SIMPLE) {
         pre = fma_t(wq0, r[MP], pre);
       } else {
-        for (int q = 0; q < Q; ++q) pre = fma_t(wqs[q * BW2_TH + tid], r[MP + q], pre);
+        if (QREG) {
+#pragma unroll
+          for (int q = 0; q < QN; ++q)
+            if (q < Q) { fq[q] = r[MP + q]; pre = fma_t(wqr[q], fq[q], pre); }
+        } else {
+          for (int q = 0; q < Q; ++q) pre = fma_t(wqs[q * BW2_TH + tid], r[MP + q], pre);
+        }
         if (NL) { lab = labs[cur * BW2_ROWS + p]; pre += tabs[lab * BW2_TH + tid]; }
       }
       const T sg = sigmoid_acc<T>(pre);
@@ -791,7 +849,13 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
       if (SIMPLE) {
         gwq0 = fma_t(r[MP], gp, gwq0);
       } else {
-        for (int q = 0; q < Q; ++q) gwqs[q * BW2_TH + tid] = fma_t(r[MP + q], gp, gwqs[q * BW2_TH + tid]);
+        if (QREG) {
+#pragma unroll
+          for (int q = 0; q < QN; ++q)
+            if (q < Q) gwqr[q] = fma_t(fq[q], gp, gwqr[q]);
+        } else {
+          for (int q = 0; q < Q; ++q) gwqs[q * BW2_TH + tid] = fma_t(r[MP + q], gp, gwqs[q * BW2_TH + tid]);
+        }
         if (NL) gtabs[lab * BW2_TH + tid] += gp;
       }
     }
@@ -827,7 +891,13 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
     if (SIMPLE) {
       atomic_add_t<T>(a.gpk + a.L.wq + (size_t)(2 * s.F) * s.Hp + hh, gwq0);
     } else {
-      for (int q = 0; q < Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
+      if (QREG) {
+#pragma unroll
+        for (int q = 0; q < QN; ++q)
+          if (q < Q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqr[q]);
+      } else {
+        for (int q = 0; q < Q; ++q) atomic_add_t<T>(a.gpk + a.L.wq + (size_t)q * s.Hp + hh, gwqs[q * BW2_TH + tid]);
+      }
       for (int l = 0; l < NL; ++l) atomic_add_t<T>(a.gpk + a.L.tab + (size_t)l * s.Hp + hh, gtabs[l * BW2_TH + tid]);
     }
   }
