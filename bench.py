@@ -335,9 +335,38 @@ def arm_ours(args):
                  ms_per_step=e2e_s / args.steps * 1e3),
         gpu_launches=int(launches.value), clocks=clocks, roofline=roofline,
         equivariance_err=equivariance_error(mod, feats, coors, dtype, dev))
+    if world == 1:
+        out["train_step"] = train_step_probe(args.workload, dev, pairs_rank)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_subprocess(args.workload)
     print(json.dumps(out))
+
+
+def train_step_probe(workload, dev, pairs):
+    """Informational (not part of the metric): one forward + backward of the same workload through the autograd
+    bridge (fp32 recompute-in-backward kernels, egnn_layer_backward), median of 3 after 2 warm-ups."""
+    try:
+        mod, feats, coors = build_workload(workload, torch.float32, dev, seed=0)
+        mod.requires_grad_(True)
+        f = feats.to(dev, torch.float32).requires_grad_(True)
+        x = coors.to(dev).requires_grad_(True)
+        ts = []
+        with torch.enable_grad():
+            for it in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fo, xo = mod(f, x)
+                (fo.sum() + xo.sum()).backward()
+                b.record()
+                torch.cuda.synchronize(dev)
+                if it >= 2:
+                    ts.append(a.elapsed_time(b))
+                mod.zero_grad(set_to_none=True)
+                f.grad = x.grad = None
+        ms = sorted(ts)[1]
+        return dict(ms_per_step=ms, pairs_per_s=pairs / ms * 1e3, dtype="f32", what="forward + backward, device-resident")
+    except Exception as e:  # noqa: BLE001  (a probe must never break the benchmark line)
+        return dict(error=f"{type(e).__name__}: {e}"[:200])
 
 
 def arm_reference(args):
