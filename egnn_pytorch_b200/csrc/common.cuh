@@ -82,6 +82,31 @@ template <typename T> __device__ __forceinline__ T sq_acc(T a, T acc);
 template <> __device__ __forceinline__ float sq_acc<float>(float a, float acc) { return __fadd_rn(acc, __fmul_rn(a, a)); }
 template <> __device__ __forceinline__ double sq_acc<double>(double a, double acc) { return __dadd_rn(acc, __dmul_rn(a, a)); }
 
+// Two values that travel together through a contraction.  fp32: one 64-bit register pair and one packed FFMA2
+// (fma.rn.f32x2, the same IEEE fma per lane, so results are bit-identical to scalar code) per update -- the SIMT pair
+// kernels are issue-bound and most of their instructions are these contractions; fp64: two DFMAs.
+template <typename T> struct Pk2;
+template <> struct Pk2<float> {
+  unsigned long long v;
+  __device__ __forceinline__ static Pk2 make(float lo, float hi) {
+    Pk2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+  }
+  __device__ __forceinline__ void fma(const Pk2& a, const Pk2& b) {       // this += a * b
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(v) : "l"(a.v), "l"(b.v));
+  }
+  __device__ __forceinline__ float lo() const { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return x; }
+  __device__ __forceinline__ float hi() const { float x, y; asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); return y; }
+};
+template <> struct Pk2<double> {
+  double x, y;
+  __device__ __forceinline__ static Pk2 make(double lo, double hi) { Pk2 r; r.x = lo; r.y = hi; return r; }
+  __device__ __forceinline__ void fma(const Pk2& a, const Pk2& b) { x = ::fma(a.x, b.x, x); y = ::fma(a.y, b.y, y); }
+  __device__ __forceinline__ double lo() const { return x; }
+  __device__ __forceinline__ double hi() const { return y; }
+};
+
 // 4 consecutive elements, 4-element aligned.
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {

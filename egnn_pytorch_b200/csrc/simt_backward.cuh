@@ -69,6 +69,14 @@ struct BwdArgs {
 
 template <typename T> __device__ __forceinline__ T dsilu_from(T x, T sg) { return sg * (T(1) + x * (T(1) - sg)); }
 
+// sigmoid for the bwd2 kernels: ex2.approx.ftz directly (no range fix-up: +-inf / 0 are the right limits here).
+__device__ __forceinline__ float sigmoid_bw(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  return __fdividef(1.0f, 1.0f + e);
+}
+__device__ __forceinline__ double sigmoid_bw(double x) { return 1.0 / (1.0 + exp(-x)); }
+
 // Record index of pair (b, i, slot).  kNN: row-major (b, i, slot).  Dense: (b, j, i) -- "column-major" -- so that the
 // records of 32 consecutive rows i for one neighbour j are contiguous, which is what a bwd2 CTA streams.
 template <bool KNN>
@@ -237,9 +245,9 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
     const T* Brow = a.P + ((size_t)b * s.N + j) * a.ldP + s.Hp;
     const T* tabrow = pk + a.L.tab + (size_t)lab * s.Hp;
 
-    T acc[MP];
+    Pk2<T> accp[MP / 2];
 #pragma unroll
-    for (int o = 0; o < MP; ++o) acc[o] = T(0);
+    for (int o = 0; o < MP / 2; ++o) accp[o] = Pk2<T>::make(T(0), T(0));
 
     // ---- forward recompute of W2 silu(pre1) (identical to pair_kernel), unless the caller already did it
     if (a.pre2) {
@@ -250,8 +258,8 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
         for (int o = 0; o < MP; o += 4) {
           Vec4<T> v;
           v.load_g(src + o);
-#pragma unroll
-          for (int z = 0; z < 4; ++z) acc[o + z] = v.v[z];
+          accp[o / 2] = Pk2<T>::make(v.v[0], v.v[1]);
+          accp[o / 2 + 1] = Pk2<T>::make(v.v[2], v.v[3]);
         }
       }
     }
@@ -306,18 +314,22 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const T hdn = silu_acc<T>(pre[u]);
+          const T hv = silu_acc<T>(pre[u]);             // egnn_pytorch.py:181
+          const Pk2<T> hdn = Pk2<T>::make(hv, hv);
           const T* w2 = W2s + (cc + u) * MP;
 #pragma unroll
           for (int v4 = 0; v4 < MP; v4 += 4) {
             Vec4<T> wv;
             wv.load(w2 + v4);
-#pragma unroll
-            for (int z = 0; z < 4; ++z) acc[v4 + z] = fma_t(hdn, wv.v[z], acc[v4 + z]);
+            accp[v4 / 2].fma(hdn, Pk2<T>::make(wv.v[0], wv.v[1]));
+            accp[v4 / 2 + 1].fma(hdn, Pk2<T>::make(wv.v[2], wv.v[3]));
           }
         }
       }
     }
+    T acc[MP];
+#pragma unroll
+    for (int o = 0; o < MP; o += 2) { acc[o] = accp[o / 2].lo(); acc[o + 1] = accp[o / 2].hi(); }
 
     // ---- pair epilogue, forward
     T mm[MP];
@@ -562,11 +574,11 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
     tabs[l * BW2_TH + tid] = hv ? pk[a.L.tab + (size_t)l * s.Hp + hh] : T(0);
     gtabs[l * BW2_TH + tid] = T(0);
   }
-  T w2r[MP], gW2[MP];
+  Pk2<T> w2p[MP / 2], gW2p[MP / 2];
 #pragma unroll
-  for (int o = 0; o < MP; ++o) {
-    w2r[o] = hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0);
-    gW2[o] = T(0);
+  for (int o = 0; o < MP; o += 2) {
+    w2p[o / 2] = Pk2<T>::make(hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0), hv ? pk[a.L.w2t + (size_t)hh * MP + o + 1] : T(0));
+    gW2p[o / 2] = Pk2<T>::make(T(0), T(0));
   }
   const T wq0 = hv ? pk[a.L.wq + (size_t)(2 * s.F) * s.Hp + hh] : T(0);
   T gwq0 = T(0);
@@ -639,19 +651,21 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           }
           if (NL) { lab = lb[cur * BW2_PB + p]; pre += tabs[lab * BW2_TH + tid]; }
         }
-        const T sg = sigmoid_acc<T>(pre);
+        const T sg = sigmoid_bw(pre);
         const T a1 = pre * sg;
-        T ga1 = T(0);
+        Pk2<T> ga1p = Pk2<T>::make(T(0), T(0));
+        const Pk2<T> a1p = Pk2<T>::make(a1, a1);
 #pragma unroll
         for (int o = 0; o < MP; o += 4) {
           Vec4<T> gv;
           gv.load(r + o);
-#pragma unroll
-          for (int z = 0; z < 4; ++z) {
-            ga1 = fma_t(w2r[o + z], gv.v[z], ga1);
-            gW2[o + z] = fma_t(a1, gv.v[z], gW2[o + z]);
-          }
+          const Pk2<T> g01 = Pk2<T>::make(gv.v[0], gv.v[1]), g23 = Pk2<T>::make(gv.v[2], gv.v[3]);
+          ga1p.fma(w2p[o / 2], g01);
+          ga1p.fma(w2p[o / 2 + 1], g23);
+          gW2p[o / 2].fma(a1p, g01);
+          gW2p[o / 2 + 1].fma(a1p, g23);
         }
+        const T ga1 = ga1p.lo() + ga1p.hi();
         gp = ga1 * dsilu_from<T>(pre, sg);
         gA += gp;
         if (hv) atomic_add_t<T>(a.gP + ((size_t)b * N + j) * a.ldP + s.Hp + hh, gp);
@@ -696,7 +710,10 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
   if (hv) {
     if (cur_row >= 0) a.gP[((size_t)b * N + i0 + cur_row) * a.ldP + hh] = gA;
 #pragma unroll
-    for (int o = 0; o < MP; ++o) atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2[o]);
+    for (int o = 0; o < MP; o += 2) {
+      atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2p[o / 2].lo());
+      atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o + 1, gW2p[o / 2].hi());
+    }
     if (SIMPLE) {
       atomic_add_t<T>(a.gpk + a.L.wq + (size_t)(2 * s.F) * s.Hp + hh, gwq0);
     } else {
@@ -771,11 +788,12 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
   }
   for (int x = tid; x < 2 * BW2_ROWS * R; x += BW2_TH) recs[x] = T(0);     // rows >= nrows stay zero
   if (tid < 2 * BW2_ROWS) labs[tid] = 0;
-  T w2r[MP], gW2[MP], gA[BW2_ROWS];
+  T gA[BW2_ROWS];
+  Pk2<T> w2p[MP / 2], gW2p[MP / 2];
 #pragma unroll
-  for (int o = 0; o < MP; ++o) {
-    w2r[o] = hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0);
-    gW2[o] = T(0);
+  for (int o = 0; o < MP; o += 2) {
+    w2p[o / 2] = Pk2<T>::make(hv ? pk[a.L.w2t + (size_t)hh * MP + o] : T(0), hv ? pk[a.L.w2t + (size_t)hh * MP + o + 1] : T(0));
+    gW2p[o / 2] = Pk2<T>::make(T(0), T(0));
   }
 #pragma unroll
   for (int p = 0; p < BW2_ROWS; ++p) gA[p] = T(0);
@@ -829,19 +847,21 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
         }
         if (NL) { lab = labs[cur * BW2_ROWS + p]; pre += tabs[lab * BW2_TH + tid]; }
       }
-      const T sg = sigmoid_acc<T>(pre);
+      const T sg = sigmoid_bw(pre);
       const T a1 = pre * sg;
-      T ga1 = T(0);
+      Pk2<T> ga1p = Pk2<T>::make(T(0), T(0));
+      const Pk2<T> a1p = Pk2<T>::make(a1, a1);
 #pragma unroll
       for (int o = 0; o < MP; o += 4) {
         Vec4<T> gv;
         gv.load(r + o);
-#pragma unroll
-        for (int z = 0; z < 4; ++z) {
-          ga1 = fma_t(w2r[o + z], gv.v[z], ga1);
-          gW2[o + z] = fma_t(a1, gv.v[z], gW2[o + z]);
-        }
+        const Pk2<T> g01 = Pk2<T>::make(gv.v[0], gv.v[1]), g23 = Pk2<T>::make(gv.v[2], gv.v[3]);
+        ga1p.fma(w2p[o / 2], g01);
+        ga1p.fma(w2p[o / 2 + 1], g23);
+        gW2p[o / 2].fma(a1p, g01);
+        gW2p[o / 2 + 1].fma(a1p, g23);
       }
+      const T ga1 = ga1p.lo() + ga1p.hi();
       const T gp = ga1 * dsilu_from<T>(pre, sg);
       gA[p] += gp;
       gB += gp;
@@ -887,7 +907,10 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
     for (int p = 0; p < BW2_ROWS; ++p)
       if (p < nrows) a.gP[((size_t)b * N + i0 + p) * a.ldP + hh] = gA[p];
 #pragma unroll
-    for (int o = 0; o < MP; ++o) atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2[o]);
+    for (int o = 0; o < MP; o += 2) {
+      atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o, gW2p[o / 2].lo());
+      atomic_add_t<T>(a.gpk + a.L.w2t + (size_t)hh * MP + o + 1, gW2p[o / 2].hi());
+    }
     if (SIMPLE) {
       atomic_add_t<T>(a.gpk + a.L.wq + (size_t)(2 * s.F) * s.Hp + hh, gwq0);
     } else {

@@ -369,9 +369,9 @@ pair_kernel(const PairArgs<T> a) {
     const T* Brow = a.P + ((size_t)b * s.N + j) * a.ldP + s.Hp;
     const T* tabrow = pk + a.L.tab + (size_t)lab * s.Hp;
 
-    T acc[MP];
+    Pk2<T> accp[MP / 2];
 #pragma unroll
-    for (int o = 0; o < MP; ++o) acc[o] = T(0);
+    for (int o = 0; o < MP / 2; ++o) accp[o] = Pk2<T>::make(T(0), T(0));
 
     for (int c0 = 0; c0 < s.Hp; c0 += PAIR_CH) {
       const int cn = min(PAIR_CH, s.Hp - c0);      // multiple of 8
@@ -426,18 +426,22 @@ pair_kernel(const PairArgs<T> a) {
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const T hdn = silu_acc<T>(pre[u]);            // egnn_pytorch.py:181
+          const T hv = silu_acc<T>(pre[u]);             // egnn_pytorch.py:181
+          const Pk2<T> hdn = Pk2<T>::make(hv, hv);
           const T* w2 = W2s + (cc + u) * MP;
 #pragma unroll
           for (int v4 = 0; v4 < MP; v4 += 4) {
             Vec4<T> wv;
             wv.load(w2 + v4);
-#pragma unroll
-            for (int z = 0; z < 4; ++z) acc[v4 + z] = fma_t(hdn, wv.v[z], acc[v4 + z]);
+            accp[v4 / 2].fma(hdn, Pk2<T>::make(wv.v[0], wv.v[1]));
+            accp[v4 / 2 + 1].fma(hdn, Pk2<T>::make(wv.v[2], wv.v[3]));
           }
         }
       }
     }
+    T acc[MP];
+#pragma unroll
+    for (int o = 0; o < MP; o += 2) { acc[o] = accp[o / 2].lo(); acc[o + 1] = accp[o / 2].hi(); }
 
     // ---- epilogue for this pair: m_ij, gate, coordinate weight, masks (egnn_pytorch.py:287-322)
     T mm[MP];
@@ -613,11 +617,11 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
       }
     }
 
-    T acc[PP][MP];
+    Pk2<T> accp[PP][MP / 2];
 #pragma unroll
     for (int p = 0; p < PP; ++p)
 #pragma unroll
-      for (int o = 0; o < MP; ++o) acc[p][o] = T(0);
+      for (int o = 0; o < MP / 2; ++o) accp[p][o] = Pk2<T>::make(T(0), T(0));
 
     int c_begin = 0, c_end = s.Hp;
     if (a.phase == 1) {
@@ -681,21 +685,31 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const T* w2 = W2s + (cc + u) * MP;
-          T hdn[PP];
+          Pk2<T> hdn[PP];
 #pragma unroll
-          for (int p = 0; p < PP; ++p) hdn[p] = silu_acc<T>(pre[p][u]);
+          for (int p = 0; p < PP; ++p) {
+            const T hv = silu_acc<T>(pre[p][u]);
+            hdn[p] = Pk2<T>::make(hv, hv);
+          }
 #pragma unroll
           for (int v4 = 0; v4 < MP; v4 += 4) {
             Vec4<T> wv;
             wv.load(w2 + v4);
+            const Pk2<T> w01 = Pk2<T>::make(wv.v[0], wv.v[1]), w23 = Pk2<T>::make(wv.v[2], wv.v[3]);
 #pragma unroll
-            for (int p = 0; p < PP; ++p)
-#pragma unroll
-              for (int z = 0; z < 4; ++z) acc[p][v4 + z] = fma_t(hdn[p], wv.v[z], acc[p][v4 + z]);
+            for (int p = 0; p < PP; ++p) {
+              accp[p][v4 / 2].fma(hdn[p], w01);
+              accp[p][v4 / 2 + 1].fma(hdn[p], w23);
+            }
           }
         }
       }
     }
+    T acc[PP][MP];
+#pragma unroll
+    for (int p = 0; p < PP; ++p)
+#pragma unroll
+      for (int o = 0; o < MP; o += 2) { acc[p][o] = accp[p][o / 2].lo(); acc[p][o + 1] = accp[p][o / 2].hi(); }
 
     if (a.phase != 0) {
       // split hidden axis: partial sums go through global memory, summed in split order (deterministic)
