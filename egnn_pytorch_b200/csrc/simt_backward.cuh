@@ -682,7 +682,7 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           if (NL) gtabs[lab * BW2_TH + tid] += gp;
         }
       }
-      gps[p * BW2_TH + tid] = gp;
+      gps[p * BW2_TH + tid] = SIMPLE ? wq0 * gp : gp;      // SIMPLE: the tile holds Wq[h] * g_pre1 already
     }
     __syncthreads();                                   // gps complete
     {
@@ -692,7 +692,14 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
       for (int q = 0; q < Q; ++q) {
         const T* wrow = wqs + q * BW2_TH + qt * 32;
         T v = T(0);
-        if (live) {
+        if (live && SIMPLE) {
+#pragma unroll
+          for (int kx = 0; kx < 8; ++kx) {
+            Vec4<T> t;
+            t.load(grow + 4 * ((kx + lane) & 7));
+            v += (t.v[0] + t.v[1]) + (t.v[2] + t.v[3]);
+          }
+        } else if (live) {
 #pragma unroll 8
           for (int kx = 0; kx < 32; ++kx) {
             const int kk = (kx + lane) & 31;
@@ -865,7 +872,7 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
       const T gp = ga1 * dsilu_from<T>(pre, sg);
       gA[p] += gp;
       gB += gp;
-      gps[p * BW2_TH + tid] = gp;
+      gps[p * BW2_TH + tid] = SIMPLE ? wq0 * gp : gp;      // SIMPLE: the tile holds Wq[h] * g_pre1 already
       if (SIMPLE) {
         gwq0 = fma_t(r[MP], gp, gwq0);
       } else {
@@ -889,10 +896,19 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
       for (int q = 0; q < Q; ++q) {
         const T* wrow = wqs + q * BW2_TH + qt * 32;
         T v = T(0);
+        if (SIMPLE) {                                   // plain row sum, 4 values per load, rotated start per lane
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            Vec4<T> t;
+            t.load(grow + 4 * ((k + lane) & 7));
+            v += (t.v[0] + t.v[1]) + (t.v[2] + t.v[3]);
+          }
+        } else {
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-          const int kk = (k + lane) & 31;
-          v = fma_t(wrow[kk], grow[kk], v);
+          for (int k = 0; k < 32; ++k) {
+            const int kk = (k + lane) & 31;
+            v = fma_t(wrow[kk], grow[kk], v);
+          }
         }
         v += shfl_xor_t<T>(v, 1);
         v += shfl_xor_t<T>(v, 2);
