@@ -66,7 +66,7 @@ class LayerIO(C.Structure):
     _fields_ = [
         ("feats", C.c_void_p), ("coors", C.c_void_p), ("edges", C.c_void_p), ("edge_labels", C.c_void_p),
         ("mask", C.c_void_p), ("adj", C.c_void_p), ("feats_out", C.c_void_p), ("coors_out", C.c_void_p),
-        ("nbr_idx", C.c_void_p),
+        ("nbr_idx", C.c_void_p), ("pre2_out", C.c_void_p),
     ]
 
 

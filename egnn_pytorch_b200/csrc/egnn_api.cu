@@ -33,6 +33,7 @@ static int launch_pair_tiled(const PairArgs<T>& a, cudaStream_t st) {
   if (a.hsplit > 1) {
     PairArgs<T> a1 = a, a2 = a;
     a1.phase = 1; a2.phase = 2;
+    a1.pre2_out = nullptr;                            // partial sums; phase 2 holds the full ones
     dim3 g1(grid.x, grid.y, a.hsplit);
     pair_dense_tiled_kernel<T, MP, PP><<<g1, PAIR_THREADS, smem, st>>>(a1);
     EGNN_LAUNCH_CHECK();
@@ -100,6 +101,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   a.ld_m = s.dim + s.m;
   a.coors_out = uc ? static_cast<T*>(io.coors_out) : nullptr;
   a.hpart = reinterpret_cast<T*>(base + wl.hpart); a.hsplit = wl.hsplit; a.phase = 0;
+  a.pre2_out = (s.k == 0) ? static_cast<T*>(io.pre2_out) : nullptr;
   {
     StageTimer tm(st, STAGE_PAIR);
     if (s.k > 0) {
@@ -263,6 +265,7 @@ extern "C" int egnn_layer_forward_host(const EgnnLayerDesc* desc, const EgnnLaye
     dio.mask = nm ? reinterpret_cast<uint8_t*>(arena + off[6]) : nullptr;
     dio.adj = na ? reinterpret_cast<uint8_t*>(arena + off[7]) : nullptr;
     dio.nbr_idx = nn ? reinterpret_cast<int32_t*>(arena + off[9]) : nullptr;
+    dio.pre2_out = nullptr;
     rc = egnn_layer_forward(desc, w, packed, &dio, arena + off[8], wsb, stream);
   }
   if (rc == EGNN_OK) {

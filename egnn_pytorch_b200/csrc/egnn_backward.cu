@@ -74,6 +74,7 @@ static int launch_tiled_recompute(const BwdArgs<T>& a, T* pre2, cudaStream_t st)
   f.nbr_idx = nullptr; f.nbr_ok = nullptr; f.packed = a.packed;
   f.m_out = nullptr; f.ld_m = 0; f.coors_out = nullptr;
   f.hpart = pre2; f.hsplit = 1; f.phase = 1;
+  f.pre2_out = nullptr;
   const size_t smem = pair_tiled_smem_bytes<T>(a.s, a.L, PP);
   EGNN_TRY(opt_in_smem(pair_dense_tiled_kernel<T, MP, PP>, smem));
   dim3 grid(ceil_div(a.s.N, 4 * PP), a.s.B, 1);
@@ -83,13 +84,15 @@ static int launch_tiled_recompute(const BwdArgs<T>& a, T* pre2, cudaStream_t st)
 }
 
 template <typename T, int MP, bool KNN>
-static int launch_pair_bwd(BwdArgs<T>& a, cudaStream_t st) {
+static int launch_pair_bwd(BwdArgs<T>& a, bool saved_pre2, cudaStream_t st) {
   const Dims& s = a.s;
   if constexpr (!KNN) {
+    if (!saved_pre2) {
     T* pre2 = const_cast<T*>(a.pre2);
     const int rc = launch_tiled_recompute<T, MP, (MP == 32 && sizeof(T) == 8) ? 1 : 2>(a, pre2, st);
     if (rc == EGNN_ERR_UNSUPPORTED) a.pre2 = nullptr;
     else EGNN_TRY(rc);
+    }
   }
   const size_t smem1 = bwd1_smem_bytes<T>(s, a.L, KNN, (a.flags & EGNN_FLAG_SOFT_EDGES) != 0);
   EGNN_TRY(opt_in_smem(pair_bwd1_kernel<T, MP, KNN>, smem1));
@@ -233,19 +236,20 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
   a.packed = static_cast<const T*>(packed);
   a.g_node_in = uf ? g_node_in : nullptr; a.ld_g = dn;
   a.g_coors_out = static_cast<const T*>(gr.g_coors_out);
-  a.pre2 = s.k == 0 ? reinterpret_cast<const T*>(base + bl.pre2) : nullptr;
+  const bool saved = s.k == 0 && io.pre2_out != nullptr;     // the forward kept W2 silu(pre1) per pair
+  a.pre2 = s.k == 0 ? (saved ? static_cast<const T*>(io.pre2_out) : reinterpret_cast<const T*>(base + bl.pre2)) : nullptr;
   a.rec = rec; a.gpk = gpk; a.gP = gP; a.g_coors = g_coors;
   a.g_edges = (s.edge_dim > 0) ? static_cast<T*>(gr.g_edges) : nullptr;
   if (s.k > 0) {
     int TS = 1;
     while (TS < s.k && TS < 32) TS <<= 1;
     a.TS = TS; a.TI2 = 16;
-    if (L.MP == 16) EGNN_TRY((launch_pair_bwd<T, 16, true>(a, st)));
-    else EGNN_TRY((launch_pair_bwd<T, 32, true>(a, st)));
+    if (L.MP == 16) EGNN_TRY((launch_pair_bwd<T, 16, true>(a, false, st)));
+    else EGNN_TRY((launch_pair_bwd<T, 32, true>(a, false, st)));
   } else {
     a.TS = 32; a.TI2 = 32;
-    if (L.MP == 16) EGNN_TRY((launch_pair_bwd<T, 16, false>(a, st)));
-    else EGNN_TRY((launch_pair_bwd<T, 32, false>(a, st)));
+    if (L.MP == 16) EGNN_TRY((launch_pair_bwd<T, 16, false>(a, saved, st)));
+    else EGNN_TRY((launch_pair_bwd<T, 32, false>(a, saved, st)));
   }
 
   // ---- per-node tables reversed: A = h W1[:, :dim]^T + b1, B = h W1[:, dim:2dim]^T

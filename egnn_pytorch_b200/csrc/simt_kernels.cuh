@@ -266,6 +266,7 @@ struct PairArgs {
   // tiny graphs only (pair_dense_tiled_kernel): the hidden axis is split over gridDim.z CTAs in phase 1, which
   // store partial m_pre sums to hpart [hsplit][B][N][N][MP]; phase 2 adds them up in a fixed order and finishes.
   T* hpart; int hsplit; int phase;      // phase 0 = single pass
+  T* pre2_out;                          // dense, optional: [B,N,N][MP] W2 silu(pre1) per pair, kept for backward
 };
 
 template <typename T>
@@ -443,6 +444,11 @@ pair_kernel(const PairArgs<T> a) {
 #pragma unroll
     for (int o = 0; o < MP; o += 2) { acc[o] = accp[o / 2].lo(); acc[o + 1] = accp[o / 2].hi(); }
 
+    if (!KNN && a.pre2_out && pair_valid) {
+      T* dst = a.pre2_out + (((size_t)b * s.N + i) * s.N + j) * MP;
+#pragma unroll
+      for (int o = 0; o < MP; ++o) dst[o] = acc[o];
+    }
     // ---- epilogue for this pair: m_ij, gate, coordinate weight, masks (egnn_pytorch.py:287-322)
     T mm[MP];
 #pragma unroll
@@ -728,6 +734,15 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
         }
       }
       if (a.phase == 1) continue;
+    }
+    if (a.pre2_out) {
+#pragma unroll
+      for (int p = 0; p < PP; ++p) {
+        if (!(rvalid[p] && jv)) continue;
+        T* dst = a.pre2_out + (((size_t)b * s.N + irow[p]) * s.N + j) * MP;
+#pragma unroll
+        for (int o = 0; o < MP; ++o) dst[o] = acc[p][o];
+      }
     }
     // ---- epilogue of this j-tile for the PP rows
     const bool mask_j = a.has_mask ? (a.mask[(size_t)b * s.N + j] != 0) : true;

@@ -394,12 +394,21 @@ class EGNN(nn.Module):
             if rows is not None:       # rows outside the range keep the input values
                 f_out.copy_(f_in)
                 x_out.copy_(x_in)
+            # dense training: keep the per-pair pre-activations of edge_mlp's second SiLU (64 B per pair in fp32) so
+            # that backward need not recompute them, unless that exceeds EGNN_B200_SAVE_PAIR_MB (default 1024)
+            pre2 = None
+            if train and k == 0:
+                mp = 16 if self.m_dim <= 16 else 32
+                nbytes = b * n * n * mp * f_in.element_size()
+                if nbytes <= float(os.environ.get("EGNN_B200_SAVE_PAIR_MB", "1024")) * 2 ** 20:
+                    pre2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             io = nat.LayerIO(feats=f_in.data_ptr(), coors=x_in.data_ptr(), edges=None if e_in is None else e_in.data_ptr(),
                              edge_labels=None if l_in is None else l_in.data_ptr(),
                              mask=None if m_in is None else m_in.data_ptr(),
                              adj=None if adj_u8 is None else adj_u8.data_ptr(),
                              feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr(),
-                             nbr_idx=None if nbr is None else nbr.data_ptr())
+                             nbr_idx=None if nbr is None else nbr.data_ptr(),
+                             pre2_out=None if pre2 is None else pre2.data_ptr())
             # training keeps the workspace (per-node tables, pooled messages, neighbour lists) for backward
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if train else _workspace(dev, ws_bytes)
             nat.check("egnn_layer_forward",
@@ -411,7 +420,7 @@ class EGNN(nn.Module):
             return outs
         saved = dict(dev=dev, kdt=kdt, cdt=cdt, desc=desc, w=w, packed=packed, io=io, ws=ws, tensors=T,
                      f_in=f_in, x_in=x_in, e_in=e_in, param_fields=param_fields,
-                     keep=(m_in, l_in, adj_u8, nbr, lab_w))            # everything io points at stays alive
+                     keep=(m_in, l_in, adj_u8, nbr, lab_w, pre2))      # everything io points at stays alive
         return outs + (saved,)
 
 

@@ -97,6 +97,17 @@ def test_grads_fp32(name):
     compare(got, want, _tol(case, torch.float32), f"{name} fp32 vs oracle")
 
 
+@pytest.mark.parametrize("name", ["dense_everything", "dense_edges", "c1_dim512_xavier", "net_dense_feats"])
+def test_grads_with_recompute_instead_of_saved_pair_activations(name, monkeypatch):
+    """Dense training keeps 64 B per pair by default (EgnnLayerIO.pre2_out); with the budget set to 0 the backward
+    recomputes them with the register-tiled forward kernel -- both routes must give the same gradients."""
+    monkeypatch.setenv("EGNN_B200_SAVE_PAIR_MB", "0")
+    case = cases.build_case(cases.SPECS[name])
+    got = module_grads(case, torch.float64)
+    want = cases.flatten_grads(cases.run_oracle_grad(case))
+    compare(got, want, _tol(case, torch.float64), f"{name} (recompute) vs oracle")
+
+
 def test_cpu_tensors_and_bf16_modules_train_through_the_gpu_kernels():
     """CPU fp64 tensors (how the reference's tests call the layer) get CPU gradients; a bf16 module trains through
     the fp32 kernels and returns bf16 gradients."""
