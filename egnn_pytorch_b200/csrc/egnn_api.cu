@@ -101,7 +101,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   a.ld_m = s.dim + s.m;
   a.coors_out = uc ? static_cast<T*>(io.coors_out) : nullptr;
   a.hpart = reinterpret_cast<T*>(base + wl.hpart); a.hsplit = wl.hsplit; a.phase = 0;
-  a.pre2_out = (s.k == 0) ? static_cast<T*>(io.pre2_out) : nullptr;
+  a.pre2_out = static_cast<T*>(io.pre2_out);
   {
     StageTimer tm(st, STAGE_PAIR);
     if (s.k > 0) {

@@ -236,8 +236,9 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
   a.packed = static_cast<const T*>(packed);
   a.g_node_in = uf ? g_node_in : nullptr; a.ld_g = dn;
   a.g_coors_out = static_cast<const T*>(gr.g_coors_out);
-  const bool saved = s.k == 0 && io.pre2_out != nullptr;     // the forward kept W2 silu(pre1) per pair
-  a.pre2 = s.k == 0 ? (saved ? static_cast<const T*>(io.pre2_out) : reinterpret_cast<const T*>(base + bl.pre2)) : nullptr;
+  const bool saved = io.pre2_out != nullptr;                 // the forward kept W2 silu(pre1) per pair
+  a.pre2 = saved ? static_cast<const T*>(io.pre2_out)
+                 : (s.k == 0 ? reinterpret_cast<const T*>(base + bl.pre2) : nullptr);
   a.rec = rec; a.gpk = gpk; a.gP = gP; a.g_coors = g_coors;
   a.g_edges = (s.edge_dim > 0) ? static_cast<T*>(gr.g_edges) : nullptr;
   if (s.k > 0) {

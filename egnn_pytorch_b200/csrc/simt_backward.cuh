@@ -58,8 +58,9 @@ struct BwdArgs {
   const T* packed;
   const T* g_node_in; int ld_g;   // [M][dim+m]; dL/dm_i = columns dim..dim+m  (null when !update_feats)
   const T* g_coors_out;           // [B,N,C]
-  const T* pre2;                  // dense only, optional: W2 silu(pre1) per pair, row-major [B,N,N][MP], recomputed by the
-                                  // register-tiled forward kernel; null = bwd1 recomputes it itself
+  const T* pre2;                  // optional: W2 silu(pre1) per pair, row-major [B,N,J][MP]: saved by the forward
+                                  // (EgnnLayerIO.pre2_out) or, dense only, recomputed by the register-tiled forward
+                                  // kernel; null = bwd1 recomputes it itself
   T* rec;                         // [pairs][R]
   T* gpk;                         // gradient accumulators in SimtPackLayout order (zeroed by the caller)
   T* gP;                          // [M][2*Hp]: dL/dA | dL/dB (zeroed by the caller)
@@ -252,8 +253,8 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
     // ---- forward recompute of W2 silu(pre1) (identical to pair_kernel), unless the caller already did it
     if (a.pre2) {
       __syncthreads();                               // tiles of the previous iteration fully consumed
-      if (pair_exists) {
-        const T* src = a.pre2 + (node_i * s.N + sidx) * MP;
+      if (pair_valid) {                              // (empty slots were never stored: keep their zeros)
+        const T* src = a.pre2 + (node_i * (size_t)J + sidx) * MP;
 #pragma unroll
         for (int o = 0; o < MP; o += 4) {
           Vec4<T> v;

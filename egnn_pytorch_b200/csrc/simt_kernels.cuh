@@ -266,7 +266,7 @@ struct PairArgs {
   // tiny graphs only (pair_dense_tiled_kernel): the hidden axis is split over gridDim.z CTAs in phase 1, which
   // store partial m_pre sums to hpart [hsplit][B][N][N][MP]; phase 2 adds them up in a fixed order and finishes.
   T* hpart; int hsplit; int phase;      // phase 0 = single pass
-  T* pre2_out;                          // dense, optional: [B,N,N][MP] W2 silu(pre1) per pair, kept for backward
+  T* pre2_out;                          // optional: [B,N,J][MP] W2 silu(pre1) per pair (J = N dense, k lists), kept for backward
 };
 
 template <typename T>
@@ -444,8 +444,8 @@ pair_kernel(const PairArgs<T> a) {
 #pragma unroll
     for (int o = 0; o < MP; o += 2) { acc[o] = accp[o / 2].lo(); acc[o + 1] = accp[o / 2].hi(); }
 
-    if (!KNN && a.pre2_out && pair_valid) {
-      T* dst = a.pre2_out + (((size_t)b * s.N + i) * s.N + j) * MP;
+    if (a.pre2_out && pair_valid) {                  // kept for backward: [B,N,J][MP], J = N (dense) or k
+      T* dst = a.pre2_out + (KNN ? ((size_t)b * s.N + i) * s.k + sidx : ((size_t)b * s.N + i) * s.N + j) * MP;
 #pragma unroll
       for (int o = 0; o < MP; ++o) dst[o] = acc[o];
     }

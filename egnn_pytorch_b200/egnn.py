@@ -394,12 +394,12 @@ class EGNN(nn.Module):
             if rows is not None:       # rows outside the range keep the input values
                 f_out.copy_(f_in)
                 x_out.copy_(x_in)
-            # dense training: keep the per-pair pre-activations of edge_mlp's second SiLU (64 B per pair in fp32) so
+            # training: keep the per-pair pre-activations of edge_mlp's second SiLU (64 B per pair in fp32) so
             # that backward need not recompute them, unless that exceeds EGNN_B200_SAVE_PAIR_MB (default 1024)
             pre2 = None
-            if train and k == 0:
+            if train:
                 mp = 16 if self.m_dim <= 16 else 32
-                nbytes = b * n * n * mp * f_in.element_size()
+                nbytes = b * n * (k if k > 0 else n) * mp * f_in.element_size()
                 if nbytes <= float(os.environ.get("EGNN_B200_SAVE_PAIR_MB", "1024")) * 2 ** 20:
                     pre2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             io = nat.LayerIO(feats=f_in.data_ptr(), coors=x_in.data_ptr(), edges=None if e_in is None else e_in.data_ptr(),

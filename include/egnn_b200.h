@@ -125,10 +125,11 @@ typedef struct EgnnLayerIO {
   const int32_t* nbr_idx;    /* optional, k > 0 only: caller-supplied neighbour lists [B, N, k] (edge-list
                                 mode): the distance/top-k pass is skipped.  An entry
                                 < 0 is an empty slot and never contributes.  NULL = select as the reference does. */
-  void*          pre2_out;   /* optional, dense (k == 0) fp32/fp64 training only: [B, N, N, MP] (MP = 16 when m_dim <= 16,
-                                else 32).  egnn_layer_forward stores the per-pair pre-activation of edge_mlp's second
-                                SiLU there; egnn_layer_backward, given the same pointer, skips recomputing it -- a speed /
-                                memory trade (64 B per pair in fp32).  NULL = nothing stored, backward recomputes. */
+  void*          pre2_out;   /* optional, fp32/fp64 training only: [B, N, J, MP] with J = N (dense) or k (neighbour lists)
+                                and MP = 16 when m_dim <= 16, else 32.  egnn_layer_forward stores the per-pair
+                                pre-activation of edge_mlp's second SiLU there; egnn_layer_backward, given the same
+                                pointer, skips recomputing it -- a speed / memory trade (64 B per pair in fp32).
+                                NULL = nothing stored, backward recomputes. */
 } EgnnLayerIO;
 
 int         egnn_abi_version(void);

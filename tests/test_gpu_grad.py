@@ -97,7 +97,8 @@ def test_grads_fp32(name):
     compare(got, want, _tol(case, torch.float32), f"{name} fp32 vs oracle")
 
 
-@pytest.mark.parametrize("name", ["dense_everything", "dense_edges", "c1_dim512_xavier", "net_dense_feats"])
+@pytest.mark.parametrize("name", ["dense_everything", "dense_edges", "c1_dim512_xavier", "net_dense_feats", "knn_edges_mask",
+                                  "net_c5_xavier"])
 def test_grads_with_recompute_instead_of_saved_pair_activations(name, monkeypatch):
     """Dense training keeps 64 B per pair by default (EgnnLayerIO.pre2_out); with the budget set to 0 the backward
     recomputes them with the register-tiled forward kernel -- both routes must give the same gradients."""
@@ -187,3 +188,40 @@ def test_backward_c2_shape_runs_and_matches_directional_derivative():
     fdw = (hi - lo) / (2 * eps)
     anw = float((w.grad * vw).sum())
     assert abs(fdw - anw) <= 1e-5 * max(1.0, abs(anw)), (fdw, anw)
+
+
+def test_edge_list_mode_with_empty_slots_matches_directional_derivative():
+    """`neighbors=` lists with -1 (empty) slots: analytic gradients along a random direction against a central
+    difference of the CUDA forward itself (fp64)."""
+    from egnn_pytorch_b200 import EGNN
+    torch.manual_seed(3)
+    B, N, d, k = 2, 24, 16, 6
+    mod = EGNN(dim=d, edge_dim=2, norm_coors=True, m_pool_method="mean").double().cuda()
+    for p in mod.parameters():                      # the reference's 1e-3 init hides errors: use O(1) weights
+        if p.dim() == 2:
+            torch.nn.init.xavier_normal_(p)
+    feats = torch.randn(B, N, d, device="cuda", dtype=torch.float64)
+    coors = torch.randn(B, N, 3, device="cuda", dtype=torch.float64)
+    edges = torch.randn(B, N, N, 2, device="cuda", dtype=torch.float64)
+    mask = torch.ones(B, N, dtype=torch.bool, device="cuda")
+    mask[1, -3:] = False
+    nbrs = torch.stack([torch.stack([torch.randperm(N)[:k] for _ in range(N)]) for _ in range(B)]).int().cuda()
+    nbrs[:, ::3, -2:] = -1                          # every third node has two empty slots
+    nbrs[0, 5, :] = -1                              # and one node has no neighbours at all
+    gf, gx = torch.randn_like(feats), torch.randn_like(coors)
+
+    def loss(f, x, e):
+        fo, xo = mod(f, x, e, mask=mask, neighbors=nbrs)
+        return (fo * gf).sum() + (xo * gx).sum()
+
+    fr, xr, er = (t.clone().requires_grad_(True) for t in (feats, coors, edges))
+    with torch.enable_grad():
+        loss(fr, xr, er).backward()
+    vf, vx, ve = torch.randn_like(feats), torch.randn_like(coors), torch.randn_like(edges)
+    eps = 1e-6
+    fd = float(loss(feats + eps * vf, coors + eps * vx, edges + eps * ve) -
+               loss(feats - eps * vf, coors - eps * vx, edges - eps * ve)) / (2 * eps)
+    an = float((fr.grad * vf).sum() + (xr.grad * vx).sum() + (er.grad * ve).sum())
+    assert np.isfinite(an) and abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (fd, an)
+    for p in mod.parameters():
+        assert torch.isfinite(p.grad).all()
