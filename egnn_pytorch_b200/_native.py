@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EGNN_ABI_VERSION 1
+#define EGNN_ABI_VERSION 2   /* 2: EgnnLayerIO grew nbr_idx + pre2_out; backward entry points added */
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define EGNN_OK                 0

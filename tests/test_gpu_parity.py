@@ -147,7 +147,7 @@ def test_host_buffer_entry_matches_device_entry():
     T = st["tensors"]
     packed = next(iter(st["packed"].values()))
     B, N, d = ins["feats"].shape
-    desc = nat.LayerDesc(abi_version=1, dtype=nat.DTYPE_F32, B=B, N=N, C=3, dim=d, edge_dim=mod.edge_dim, label_dim=0,
+    desc = nat.LayerDesc(abi_version=nat.ABI_VERSION, dtype=nat.DTYPE_F32, B=B, N=N, C=3, dim=d, edge_dim=mod.edge_dim, label_dim=0,
                          num_labels=0, m_dim=16, fourier=0, k=0, flags=mod._flags(), valid_radius=3e38, clamp=0.0,
                          row_begin=0, row_end=0, reserved=0)
     w = nat.LayerWeights(**{f: (T[f].data_ptr() if f in T else None) for f in nat.WEIGHT_FIELDS})

@@ -67,7 +67,7 @@ def test_ctypes_structs_match_c_layout(nat, tmp_path):
 def test_host_side_validation_without_gpu(nat):
     lib = nat.load()
     nb = C.c_size_t()
-    good = dict(abi_version=1, dtype=nat.DTYPE_F32, B=2, N=16, C=3, dim=32, edge_dim=0, label_dim=0, num_labels=0,
+    good = dict(abi_version=nat.ABI_VERSION, dtype=nat.DTYPE_F32, B=2, N=16, C=3, dim=32, edge_dim=0, label_dim=0, num_labels=0,
                 m_dim=16, fourier=0, k=0, flags=nat.FLAG_UPDATE_FEATS | nat.FLAG_UPDATE_COORS, valid_radius=1e30,
                 clamp=0.0, row_begin=0, row_end=0, reserved=0)
     d = nat.LayerDesc(**good)
