@@ -8,6 +8,10 @@ the plumbing.
   [coors | feats] and then evaluates only its own rows (`row_sharded_layer_call`); top-k, masks and
   both j-reductions are row-local, so nothing is reduced across ranks.
 
+* Training on batch shards: every rank differentiates the loss of its own graphs; the parameter gradients are
+  the only thing exchanged -- `allreduce_gradients` sums them in a few flat buckets (one collective per
+  bucket: the whole EGNN(512) layer is 12.8 MB in fp32, i.e. one launch-latency-bound all-reduce over NVLink).
+
 The compute callable is injected, so the partition/exchange logic is testable on CPU with gloo
 (tests/test_multi_rank_cpu.py drives it with the oracle); on the GPU box it is the CUDA module.
 """
@@ -76,3 +80,41 @@ def row_sharded_layer_call(layer_fn, feats_local, coors_local, n_total: int, gro
     feats_all = full[..., c:].to(feats_local.dtype).contiguous()
     f_out, x_out = layer_fn(feats_all, coors_all, rows=(r0, r1), **kw)
     return f_out[:, r0:r1], x_out[:, r0:r1]
+
+
+def allreduce_gradients(params, group=None, average: bool = False, bucket_bytes: int = 64 << 20):
+    """Sum (or average) `.grad` of the given parameters over the ranks, in place.
+
+    Gradients are packed into flat buckets of at most `bucket_bytes` per dtype so that a layer costs one collective
+    instead of one per tensor.  Parameters whose `.grad` is None on this rank (e.g. a rank with an empty shard)
+    contribute zeros -- every rank must pass the same parameter list in the same order."""
+    world = dist.get_world_size(group)
+    params = [p for p in params if p.requires_grad]
+    by_dtype = {}
+    for p in params:
+        by_dtype.setdefault((p.dtype, p.device), []).append(p)
+    for (dtype, device), plist in by_dtype.items():
+        bucket, size = [], 0
+        buckets = []
+        for p in plist:
+            nbytes = p.numel() * p.element_size()
+            if bucket and size + nbytes > bucket_bytes:
+                buckets.append(bucket)
+                bucket, size = [], 0
+            bucket.append(p)
+            size += nbytes
+        if bucket:
+            buckets.append(bucket)
+        for bucket in buckets:
+            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in bucket])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                flat /= world
+            off = 0
+            for p in bucket:
+                g = flat[off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += p.numel()

@@ -50,6 +50,24 @@ def _worker(rank, world, port, q):
         want = cases.run_oracle(case)
         assert np.abs(f_loc.numpy() - want[0][:, r0:r1]).max() < 1e-12
         assert np.abs(x_loc.numpy() - want[1][:, r0:r1]).max() < 1e-12
+        # --- batch-sharded training: each rank differentiates its own graphs (compute = backward oracle here),
+        #     parameter gradients are summed with one bucketed all-reduce, input gradients stay local
+        case = cases.build_case(cases.SPECS["knn_edges_mask"])          # B = 3 -> shards of 2 and 1
+        gf, gx = cases.upstream_grads(case)
+        full = cases.flatten_grads(cases.run_oracle_grad(case))
+        b0, b1 = parallel.shard_range(3, rank, world)
+        from oracle import egnn_oracle_grad as G
+        ins = case["inputs"]
+        part = G.egnn_layer_backward(case["params"], case["cfg"], ins["feats"][b0:b1], ins["coors"][b0:b1],
+                                     ins["edges"][b0:b1], ins["mask"][b0:b1], None, gf[b0:b1], gx[b0:b1])
+        params = {k: torch.nn.Parameter(torch.from_numpy(np.asarray(v, np.float64))) for k, v in case["params"].items()}
+        for k, p_ in params.items():
+            p_.grad = torch.from_numpy(part["params"][k]).reshape(p_.shape).clone()
+        parallel.allreduce_gradients([params[k] for k in sorted(params)], bucket_bytes=4096)   # several buckets
+        for k, p_ in params.items():
+            assert np.abs(p_.grad.numpy() - full[f"p.{k}"].reshape(p_.shape)).max() < 1e-11, k
+        assert np.abs(part["feats"] - full["in.feats"][b0:b1]).max() < 1e-12      # inputs: no exchange needed
+        assert np.abs(part["coors"] - full["in.coors"][b0:b1]).max() < 1e-12
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
