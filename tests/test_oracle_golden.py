@@ -105,3 +105,23 @@ def test_grad_oracle_against_finite_differences():
             fd = (loss(hi) - loss(lo)) / (2 * eps)
             an = float((grads[prefix + key] * v).sum())
             assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (key, fd, an)
+
+
+def test_grad_oracle_is_equivariant():
+    """Size-independent property of the backward: for coors -> coors Q + t and the coordinate cotangent G_x -> G_x Q,
+    the loss is unchanged, so dL/dfeats and every parameter gradient are invariant and dL/dcoors rotates with Q."""
+    from oracle import egnn_oracle_grad as G
+    case = cases.build_case(cases.SPECS["knn_norm_coors"])
+    ins = case["inputs"]
+    gf, gx = cases.upstream_grads(case)
+    rs = np.random.RandomState(1)
+    q, _ = np.linalg.qr(rs.standard_normal((3, 3)))
+    t = rs.standard_normal((1, 1, 3))
+    a = G.egnn_layer_backward(case["params"], case["cfg"], ins["feats"], ins["coors"], ins.get("edges"), ins.get("mask"),
+                              None, gf, gx)
+    b = G.egnn_layer_backward(case["params"], case["cfg"], ins["feats"], ins["coors"] @ q + t, ins.get("edges"),
+                              ins.get("mask"), None, gf, gx @ q)
+    assert np.abs(a["feats"] - b["feats"]).max() < 1e-6        # (CoorsNorm's 1/eps self pair leaves ~1e-9 of noise)
+    assert np.abs(a["coors"] @ q - b["coors"]).max() < 1e-6
+    for k in a["params"]:
+        assert np.abs(a["params"][k] - b["params"][k]).max() < 1e-6 * max(1.0, np.abs(a["params"][k]).max()), k
