@@ -260,6 +260,8 @@ SPECS = {
     "net_c5_xavier":      dict(kind=NW, cfg=dict(depth=2, dim=16, num_tokens=21, num_adj_degrees=3, adj_dim=8,
                                                  only_sparse_neighbors=True, edge_dim=2), B=2, N=24, seed=56, init="xavier",
                                adj="chain", mask="padded", edges=True),
+    "net_adj_dense":      dict(kind=NW, cfg=dict(depth=2, dim=12, num_tokens=9, num_adj_degrees=2, adj_dim=3), B=2, N=11, seed=58,
+                               init="xavier", adj="chain", mask="padded"),   # degree labels on DENSE layers (no neighbour selection)
     "net_adj_random":     dict(kind=NW, cfg=dict(depth=2, dim=12, num_adj_degrees=2, adj_dim=3, only_sparse_neighbors=True),
                                B=2, N=16, seed=57, init="xavier", adj="random3d", adj_p=0.1, mask="full"),
 }
