@@ -1,4 +1,4 @@
-"""Host-side mirror of the reference's module interface for the EGNN forward hot path.
+"""Host-side mirror of the reference's module interface for the EGNN hot path (forward and backward).
 
 `EGNN` and `EGNN_Network` keep the constructor arguments, forward signatures, return values and
 state-dict keys of lucidrains/egnn-pytorch (reference egnn_pytorch/egnn_pytorch.py:148-341 and
