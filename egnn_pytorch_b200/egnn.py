@@ -274,7 +274,8 @@ class EGNN(nn.Module):
 
     def _forward_train(self, fields, feats, coors, edges, mask, adj_mat, neighbors, labels, label_emb, k_hint, rows):
         if rows is not None:
-            raise NotImplementedError("a row range cannot be differentiated; shard the batch instead")
+            raise NotImplementedError("a row range (_rows) cannot be differentiated: call it under torch.no_grad() for "
+                                      "inference, or shard the batch (parallel.batch_sharded_call) for training")
         params = [p for _, _, _, p in fields]
 
         def run():
