@@ -6,15 +6,23 @@
 One "step" = one EGNN(dim=512) layer forward over one batch (B=4 graphs x N=1024 nodes, dense
 all-pairs = 4,194,304 node pairs) of synthetic N(0,1) inputs with the reference's default init
 (BASELINE.json configs[1], SURVEY.md section 8(d) "c2").  Multi-GPU: one process per GPU under torchrun,
-every rank runs its own batch (graphs are independent units: weak scaling, no data-path collective).
+every rank runs its own batch (graphs are independent units: weak scaling, no data-path collective);
+with more than one rank the line also carries `row_sharded`: ONE graph (dense, N=8192) whose i-rows are
+split over the ranks with one all-gather of [coors | feats] -- the strong-scaling case with a collective.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job pairs/s with inputs resident in HBM, timed
 per step with CUDA events on the launch stream (L2 flushed between steps, flush not timed),
 max over ranks.  `e2e` = the same through the public module API with pinned HOST tensors
 (H2D + D2H inside the timed region).  `roofline` describes the fused edge kernel, timed live by
-the library's own CUDA-event stage brackets (egnn_profile_*).  `cpu_baseline` = the oracle on the
-host cores on a bounded sample.  `--impl reference` times the reference's algorithm on the CPU
-(the oracle port; the Python reference itself cannot travel to the GPU box).
+the library's own CUDA-event stage brackets (egnn_profile_*).  `cpu_baseline` = the UNMODIFIED
+reference's own torch forward (baseline/_ref, installed by baseline/install_ref.py) on the host cores,
+one graph of the batch at a time.  `gpu_eager_baseline` = the same unmodified
+reference in PyTorch eager on the same B200 (the ">= 10x" comparison of BASELINE.json's north_star).
+`secondary` = the other four BASELINE configurations (c1, c3, c4 at 8 graphs per GPU, c5).
+
+`--impl reference` times the reference's own torch CPU forward (kind "reference"; if baseline/_ref is
+absent, oracle/egnn_torch_port.py -- a torch restatement with the same ATen call sequence -- and kind
+"port"), all host threads, one graph of the same B=4 x N=1024 workload per step.
 """
 from __future__ import annotations
 
@@ -132,82 +140,142 @@ def compulsory_bytes(w, es):
 
 
 def equivariance_error(mod, feats, coors, dtype, device):
-    """tests/test_equivariance.py:8-34 as a number: max|feats(Rx+t) - feats(x)|, max|coors(Rx+t) - (coors(x)R+t)|."""
+    """tests/test_equivariance.py:8-34 as a number: max|feats(Rx+t) - feats(x)|, max|coors(Rx+t) - (coors(x)R+t)|,
+    reported absolute AND relative to the output magnitude (the c2 outputs are O(100): x_i + sum over 1024
+    neighbours), plus the same figure for the unmodified reference in fp32 GPU-eager on the same inputs when
+    baseline/_ref is installed."""
     g = torch.Generator().manual_seed(7)
     q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
     t = torch.randn(1, 1, 3, generator=g, dtype=torch.float64)
-    f = feats[:1].to(device, dtype)
     x = coors[:1].double()
     xr = (x @ q + t)
-    f2, c2 = mod(f, x.float().to(device))
-    f1, c1 = mod(f, xr.float().to(device))
-    ef = float((f1.double() - f2.double()).abs().max())
-    ec = float((c1.double().cpu() - (c2.double().cpu() @ q + t)).abs().max())
-    return dict(feats=ef, coors=ec)
+
+    def measure(fn, f):
+        f2, c2 = fn(f, x.float().to(device))
+        f1, c1 = fn(f, xr.float().to(device))
+        ef = float((f1.double() - f2.double()).abs().max())
+        ec = float((c1.double().cpu() - (c2.double().cpu() @ q + t)).abs().max())
+        sf, sc = float(f2.double().abs().max()), float(c2.double().abs().max())
+        return dict(feats=ef, coors=ec, feats_out_scale=sf, coors_out_scale=sc, feats_rel=ef / max(sf, 1e-30),
+                    coors_rel=ec / max(sc, 1e-30))
+
+    out = measure(mod, feats[:1].to(device, dtype))
+    out["note"] = ("absolute max error; *_rel = error / max|output|.  fp32 ulp at the coordinate output scale = "
+                   f"{float(np.spacing(np.float32(out['coors_out_scale']))):.2e}")
+    ref = load_reference()
+    if ref is not None:
+        try:
+            rmod = ref.EGNN(**WORKLOADS["c2"]["cfg"]).to(device).eval()
+            rmod.load_state_dict({k: v.float() for k, v in mod.state_dict().items()})
+            out["reference_gpu_eager_fp32"] = measure(lambda f, c: rmod(f, c), feats[:1].to(device, torch.float32))
+            del rmod
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            out["reference_gpu_eager_fp32"] = dict(error=f"{type(e).__name__}: {e}"[:160])
+    return out
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
-_CPU_JOB = {}
-
-
-def _cpu_job(span):
-    from oracle import egnn_oracle as O
-    j = _CPU_JOB
-    O.egnn_layer_forward(j["params"], j["cfg"], j["feats"], j["coors"], dtype=np.float32, row_chunk=j["block"], rows=span)
-    return span[1] - span[0]
-
-
-def cpu_baseline_sample(name, target_seconds=12.0, seed=0):
-    """Time the oracle (numpy float32) on a bounded sample of the workload: `rows` i-rows of ONE
-    graph against all N neighbours, the rows split over one forked worker PROCESS per host core
-    (single-threaded BLAS in each), so both the Linear-1 GEMM and the elementwise SiLU use every
-    core.  Must run in a process that has not initialised CUDA (bench.py's GPU arm calls it through
-    `python bench.py --impl cpu-sample`)."""
-    import multiprocessing as mp
-    import cases
+# ----------------------------------------------------------------------------- the reference (baseline/_ref)
+def load_reference():
+    """The UNMODIFIED reference package installed under baseline/_ref (baseline/install_ref.py), or None."""
+    ref_dir = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "egnn_pytorch", "egnn_pytorch.py")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
     try:
-        from threadpoolctl import threadpool_limits
-    except Exception:                       # pragma: no cover
-        import contextlib
-        threadpool_limits = lambda **kw: contextlib.nullcontext()
-    w = WORKLOADS[name]
-    cores = os.cpu_count() or 1
-    spec = dict(kind="layer", cfg=w["cfg"], B=1, N=w["N"], C=w["C"], seed=seed)
-    case = cases.build_case(spec)
-    ins = case["inputs"]
-    block = 8
-    _CPU_JOB.update(params={k: np.asarray(v, np.float32) for k, v in case["params"].items()}, cfg=case["cfg"],
-                    feats=ins["feats"].astype(np.float32), coors=ins["coors"].astype(np.float32), block=block)
-    with threadpool_limits(limits=1):
-        with mp.get_context("fork").Pool(cores) as pool:
-            def run(rows):
-                spans = [(a, min(a + block, rows)) for a in range(0, rows, block)]
-                t0 = time.perf_counter()
-                pool.map(_cpu_job, spans, chunksize=1)
-                return time.perf_counter() - t0
-            probe = min(block * cores, w["N"])
-            run(probe)                               # warm-up (page faults, BLAS init in the workers)
-            dt = run(probe)
-            reps = int(max(1, min(64, target_seconds / max(dt, 1e-3))))
-            rows_list = [min(w["N"], probe)] * reps
-            if probe < w["N"]:
-                rows = int(min(w["N"], max(probe, probe * target_seconds / max(dt, 1e-3))))
-                rows_list = [max(block, rows // block * block)]
-            t = sum(run(r) for r in rows_list)
-    pairs = sum(rows_list) * w["N"]
-    return dict(value=pairs / t, unit="pairs/s", cores=cores, kind="port",
-                sample=f"{len(rows_list)} x {rows_list[0]} of {w['N']} i-rows of one graph x all {w['N']} neighbours "
-                       f"({pairs} pairs, {t:.1f} s), numpy float32 oracle, {cores} worker processes"), pairs, t
+        import egnn_pytorch
+        return egnn_pytorch
+    except Exception:       # noqa: BLE001
+        return None
+
+
+def bench_config(world, w, path=None):
+    """`config` of the JSON line -- identical in the GPU arm and in the reference arm (same workload)."""
+    return dict(workload=w["label"], per_gpu_batch=w["B"], nodes=w["N"], pairs_per_step=w["B"] * w["N"] * w["N"] * world,
+                init="reference default init (weights N(0, 1e-3), PyTorch-default biases), inputs N(0,1), seed 0",
+                l2="GPU arm: L2 flushed between timed steps (256 MiB memset, not timed); CPU reference arm: "
+                   "intermediates of one graph (21.6 GB) exceed every cache",
+                parallelism=f"batch-sharded x{world} (independent graphs, no collective)")
+
+
+class CpuReference:
+    """The reference's own dense forward on the host cores: `EGNN(dim=512)` from baseline/_ref (kind 'reference'),
+    else the torch restatement oracle/egnn_torch_port.py (kind 'port').  fp32, eval, no_grad, all host threads
+    (BASELINE.md section 3); one graph of the B=4 batch per call -- B=4 at once needs > 62 GB of intermediates."""
+
+    def __init__(self, name, seed=0):
+        self.w = WORKLOADS[name]
+        self.threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        torch.set_num_threads(self.threads)
+        torch.manual_seed(seed)
+        ref = load_reference()
+        if ref is not None:
+            self.kind = "reference"
+            self.mod = ref.EGNN(**self.w["cfg"]).eval()
+            self.fn = lambda f, x: self.mod(f, x)
+        else:
+            from oracle.egnn_torch_port import egnn_dense_forward
+            from egnn_pytorch_b200 import EGNN      # parameter container only (no forward): same init, same keys
+            self.kind = "port"
+            P = {k: v.detach().clone() for k, v in EGNN(**self.w["cfg"]).state_dict().items()}
+            self.fn = lambda f, x: egnn_dense_forward(P, f, x)
+        g = torch.Generator().manual_seed(seed + 1)
+        self.feats = torch.randn(self.w["B"], self.w["N"], self.w["cfg"]["dim"], generator=g)
+        self.coors = torch.randn(self.w["B"], self.w["N"], self.w["C"], generator=g)
+        self.n = self.w["N"]
+
+    def step(self, b):
+        """One graph (index b mod B), the first self.n nodes of it.  Returns seconds."""
+        b %= self.w["B"]
+        f, x = self.feats[b:b + 1, :self.n], self.coors[b:b + 1, :self.n]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            self.fn(f, x)
+        return time.perf_counter() - t0
+
+    def fit_budget(self, first_s, calls, budget_s):
+        """If `calls` forwards at the measured pace would exceed the budget, shrink the sampled sub-graph
+        (dense all-pairs cost is quadratic in the node count; pairs/s is what is reported)."""
+        if first_s * calls > budget_s and self.n > 256:
+            scale = (budget_s / (first_s * calls)) ** 0.5
+            self.n = max(256, int(self.n * scale) // 64 * 64)
+
+    def describe(self, calls, pairs, secs):
+        full = self.n == self.w["N"]
+        what = "one full graph" if full else f"the first {self.n} of {self.w['N']} nodes of one graph (dense all-pairs on the sub-graph)"
+        return (f"{calls} forward(s), each {what} of the B={self.w['B']} batch ({pairs} pairs, {secs:.1f} s); "
+                f"{'unmodified reference egnn_pytorch.EGNN (baseline/_ref)' if self.kind == 'reference' else 'torch restatement oracle/egnn_torch_port.py'}"
+                f", torch {torch.__version__} CPU fp32, torch.set_num_threads({self.threads})")
+
+
+def cpu_sample(name, budget_s=30.0):
+    """cpu_baseline leg of the GPU arm: 1 warm-up + up to 3 timed forwards within ~budget_s of CPU work."""
+    ref = CpuReference(name)
+    first = ref.step(0)
+    ref.fit_budget(first, 3, budget_s)
+    if ref.n != ref.w["N"]:
+        first = ref.step(0)
+    reps = int(max(1, min(3, budget_s / max(first, 1e-3) - 1)))
+    ts = [ref.step(i + 1) for i in range(reps)]
+    t = min(ts)
+    pairs = ref.n * ref.n
+    return dict(value=pairs / t, unit="pairs/s", cores=ref.threads, kind=ref.kind, nproc=os.cpu_count(),
+                seconds_per_graph=t, sample="min of " + ref.describe(reps, pairs * reps, sum(ts)))
 
 
 def cpu_baseline_subprocess(name):
-    """Run the sample in a fresh interpreter (no CUDA context, fork-safe)."""
-    res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--workload", name],
-                         capture_output=True, text=True, timeout=900)
-    for line in reversed(res.stdout.strip().splitlines()):
-        if line.startswith("{"):
-            return json.loads(line)
-    return dict(value=None, unit="pairs/s", cores=os.cpu_count(), kind="port", sample="failed: " + res.stderr[-300:])
+    """Run the sample in a fresh interpreter (no CUDA context, all host threads)."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--workload", name],
+                             capture_output=True, text=True, timeout=600)
+        for line in reversed(res.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        err = res.stderr[-300:]
+    except Exception as e:      # noqa: BLE001
+        err = f"{type(e).__name__}: {e}"
+    return dict(value=None, unit="pairs/s", cores=os.cpu_count(), kind="reference", sample="failed: " + err)
 
 
 # ----------------------------------------------------------------------------- arms
@@ -230,6 +298,109 @@ def barrier_max(world, value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def time_ms(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def gpu_eager_baseline(name, dev, ours_ms):
+    """The unmodified reference in PyTorch eager on this GPU (bf16 and fp32), same workload, same B=4 batch at once."""
+    ref = load_reference()
+    if ref is None:
+        return dict(unavailable="baseline/_ref not installed (python baseline/install_ref.py)")
+    w = WORKLOADS[name]
+    pairs = w["B"] * w["N"] * w["N"]
+    out = dict(kind="unmodified reference egnn_pytorch.EGNN (baseline/_ref), PyTorch eager, same GPU, inputs resident")
+    for tag, dt, iters in (("bf16", torch.bfloat16, 5), ("fp32", torch.float32, 3)):
+        try:
+            torch.manual_seed(0)
+            mod = ref.EGNN(**w["cfg"]).to(dt).to(dev).eval()
+            g = torch.Generator().manual_seed(1)
+            f = torch.randn(w["B"], w["N"], w["cfg"]["dim"], generator=g).to(dev, dt)
+            x = torch.randn(w["B"], w["N"], w["C"], generator=g).to(dev, dt)
+            torch.cuda.reset_peak_memory_stats(dev)
+            ms = time_ms(lambda: mod(f, x), iters, warm=2)
+            out[tag] = dict(ms_per_step=ms, pairs_per_s=pairs / ms * 1e3, peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                            speedup_of_this_repo=ms / ours_ms)
+            del mod, f, x
+        except Exception as e:      # noqa: BLE001
+            out[tag] = dict(error=f"{type(e).__name__}: {e}"[:200])
+        torch.cuda.empty_cache()
+    return out
+
+
+def secondary_configs(dev):
+    """The other BASELINE.json configurations on one GPU: ms per forward, kernel family, all-pairs/s and edges/s
+    (SURVEY.md section 8(d)), CUDA-graph replay for the launch-bound ones, and the unmodified reference in PyTorch
+    eager on the same GPU when installed.  c4 = the 8 graphs one GPU holds when B=64 is sharded over 8 GPUs."""
+    from egnn_pytorch_b200 import EGNN, EGNN_Network, GraphedForward
+    ref = load_reference()
+    g = torch.Generator().manual_seed(1)
+    rows = []
+
+    def run(name, cls, kwargs, dtype, args, kw, pairs, edges, iters, ref_iters):
+        row = dict(config=name, dtype=str(dtype)[6:])
+        try:
+            torch.manual_seed(0)
+            ours = getattr(sys.modules["egnn_pytorch_b200"], cls)(**kwargs).to(dtype).to(dev).eval()
+            ms = time_ms(lambda: ours(*args, **kw), iters)
+            layer = ours.layers[0][1] if hasattr(ours, "layers") else ours
+            row.update(ms=ms, kernel_path=layer.last_path, all_pairs_per_s=pairs / ms * 1e3,
+                       edges_per_s=None if not edges else edges / ms * 1e3)
+            if ms < 2.0:
+                gf = GraphedForward(ours, *args, **kw)
+                row["graphed_ms"] = time_ms(lambda: gf(*args), iters)
+                del gf
+            if ref is not None:
+                theirs = getattr(ref, cls)(**kwargs).to(dtype).to(dev).eval()
+                theirs.load_state_dict(ours.state_dict())
+                rms = time_ms(lambda: theirs(*args, **kw), ref_iters, warm=1)
+                o, r = ours(*args, **kw), theirs(*args, **kw)
+                row.update(ref_eager_ms=rms, speedup=rms / min(ms, row.get("graphed_ms", ms)),
+                           max_diff_feats=float((o[0].float() - r[0].float()).abs().max()),
+                           max_diff_coors=float((o[1].float() - r[1].float()).abs().max()))
+                del theirs
+        except Exception as e:      # noqa: BLE001
+            row["error"] = f"{type(e).__name__}: {e}"[:200]
+        torch.cuda.empty_cache()
+        rows.append(row)
+
+    f, x = torch.randn(1, 16, 512, generator=g).to(dev), torch.randn(1, 16, 3, generator=g).to(dev)
+    run("c1 EGNN(512) B=1 N=16", "EGNN", dict(dim=512), torch.float32, (f, x), {}, 256, None, 200, 50)
+    tok = torch.randint(0, 21, (1, 1024), generator=g).to(dev)
+    x = torch.randn(1, 1024, 3, generator=g).to(dev)
+    m = torch.ones(1, 1024, dtype=torch.bool, device=dev)
+    c3 = dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0)
+    for dt in (torch.float32, torch.bfloat16):
+        run("c3 EGNN_Network depth=3 dim=32 N=1024 k=8 mask", "EGNN_Network", c3, dt, (tok, x.to(dt)), dict(mask=m),
+            3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
+    f = torch.randn(8, 4096, 256, generator=g).to(dev, torch.bfloat16)
+    x = torch.randn(8, 4096, 3, generator=g).to(dev, torch.bfloat16)
+    e = torch.randn(8, 4096, 4096, 4, generator=g, dtype=torch.bfloat16).to(dev)
+    run("c4 EGNN(256, edge_dim=4) k=32 N=4096, 8 graphs (one GPU's share of B=64)", "EGNN",
+        dict(dim=256, edge_dim=4, num_nearest_neighbors=32), torch.bfloat16, (f, x, e), {}, 8 * 4096 * 4096, 8 * 4096 * 32, 10, 2)
+    del e, f
+    n = 8192
+    i = torch.arange(n, device=dev)
+    adj = (i[:, None] - i[None, :]).abs() <= 1
+    tok = torch.randint(0, 21, (1, n), generator=g).to(dev)
+    x = torch.randn(1, n, 3, generator=g).to(dev)
+    m = torch.ones(1, n, dtype=torch.bool, device=dev)
+    c5 = dict(num_tokens=21, dim=32, depth=3, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True)
+    for dt in (torch.float32, torch.bfloat16):
+        run("c5 EGNN_Network only_sparse num_adj_degrees=3 adj_dim=8 N=8192 chain", "EGNN_Network", c5, dt, (tok, x.to(dt)),
+            dict(adj_mat=adj, mask=m), 3 * n * n, 3 * n * 9, 10, 2)
+    return rows
 
 
 def arm_ours(args):
@@ -295,6 +466,10 @@ def arm_ours(args):
     h2d = hf.numel() * hf.element_size() + hx.numel() * hx.element_size()
     d2h = of.numel() * of.element_size() + ox.numel() * ox.element_size()
 
+    row_sharded = None
+    if world > 1:
+        row_sharded = row_sharded_probe(world, rank, dev)
+
     if rank != 0:
         return
     # ---- roofline of the fused edge kernel (stage 2), timed live by the library's event brackets
@@ -314,7 +489,8 @@ def arm_ours(args):
         bound="sfu", kernel="fused edge kernel (stage 2 of egnn_layer_forward)", path=path,
         achieved=act_rate, peak=sfu_peak, unit="Gsilu/s", frac=act_rate / sfu_peak, traffic=traffic,
         note="split formulation: the binding unit is the MUFU/SFU pipe (SURVEY.md section 8(d)); "
-             f"peak = 148 SM x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz",
+             f"peak = 148 SM x 16 MUFU/clk x {pk['sm_max_mhz']:.0f} MHz; the kernel's own instruction mix without any "
+             "synchronisation tops out at 15.0 of 16 /clk/SM (profiles/r02_pipe_bench.txt)",
         launch_ms=pair_ms, stage_ms_per_step={k: ms[i] / args.steps for i, k in
                                               enumerate(["select", "node_pre", "edge", "node_post"])},
         tensor=dict(achieved=tensor_tf, peak=pk["bf16_tflops"], unit="TFLOP/s", frac=tensor_tf / pk["bf16_tflops"],
@@ -328,18 +504,31 @@ def arm_ours(args):
         metric="EGNN fwd node-pairs/sec (dim=512 N=1024)", value=value, unit="pairs/s", n_gpus=world,
         steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
         vs_baseline=None, dtype="bf16" if path == "bf16-tcgen05" else "f32", data="synthetic",
-        config=dict(workload=w["label"], per_gpu_batch=w["B"], nodes=w["N"], pairs_per_step=pairs_rank * world,
-                    kernel_path=path, init="reference default init", l2="flushed between timed steps (256 MiB memset)",
-                    parallelism=f"batch-sharded x{world} (independent graphs, no collective)"),
+        config=bench_config(world, w), kernel_path=path,
         e2e=dict(value=e2e_value, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                  ms_per_step=e2e_s / args.steps * 1e3),
-        gpu_launches=int(launches.value), clocks=clocks, roofline=roofline,
-        equivariance_err=equivariance_error(mod, feats, coors, dtype, dev))
-    if world == 1:
+        gpu_launches=int(launches.value), clocks=clocks, roofline=roofline)
+    if row_sharded is not None:
+        out["row_sharded"] = row_sharded
+    if not args.lean:
+        out["equivariance_err"] = equivariance_error(mod, feats, coors, dtype, dev)
+    if world == 1 and not args.lean:
         out["train_step"] = train_step_probe(args.workload, dev, pairs_rank)
-    if world == 1 and not args.no_cpu_baseline:
+        out["gpu_eager_baseline"] = gpu_eager_baseline(args.workload, dev, ms_per_step)
+        out["secondary"] = secondary_configs(dev)
+    if world == 1 and not args.no_cpu_baseline and not args.lean:
         out["cpu_baseline"] = cpu_baseline_subprocess(args.workload)
     print(json.dumps(out))
+
+
+def row_sharded_probe(world, rank, dev):
+    """Strong scaling WITH a collective: one dense graph, EGNN(dim=512), N=8192, B=1,
+    its i-rows split over the ranks.  Filled in by parallel.RowShardedLayer (see there); every rank takes part."""
+    try:
+        from egnn_pytorch_b200 import parallel
+        return parallel.row_sharded_benchmark(world, rank, dev)
+    except Exception as e:      # noqa: BLE001  (a probe must never break the benchmark line)
+        return dict(error=f"{type(e).__name__}: {e}"[:300])
 
 
 def train_step_probe(workload, dev, pairs):
@@ -370,62 +559,37 @@ def train_step_probe(workload, dev, pairs):
 
 
 def arm_reference(args):
-    """The reference's algorithm on the host cores (oracle port), rank 0 only."""
+    """The reference's own torch forward on the host cores (baseline/_ref; torch restatement if absent), rank 0 only.
+    Each step = one graph of the B=4 x N=1024 batch (graphs cycle through the batch), sized down to a sub-graph only
+    if the whole --steps/--warmup run would not end within a few minutes on this host."""
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:          # under torchrun the other ranks exit 0 without work (no process group needed)
         return
     w = WORKLOADS[args.workload]
-    res, times = None, []
-    per = max(2.0, min(12.0, 60.0 / max(1, args.steps + args.warmup)))
-    for i in range(args.warmup + args.steps):
-        res, pairs, dt = cpu_baseline_sample(args.workload, target_seconds=per)
-        if i >= args.warmup:
-            times.append((pairs, dt))
-    pairs = sum(p for p, _ in times); dt = sum(t for _, t in times)
-    value = pairs / dt
-    res["value"] = value
+    ref = CpuReference(args.workload)
+    first = ref.step(0)                                  # untimed: page faults, thread pool, oneDNN/MKL init
+    calls = args.warmup + args.steps
+    ref.fit_budget(first, calls, budget_s=240.0)
+    for i in range(args.warmup):
+        ref.step(i)
+    times = [ref.step(args.warmup + i) for i in range(args.steps)]
+    pairs = ref.n * ref.n
+    dt = sum(times)
+    value = pairs * len(times) / dt
+    base = dict(value=value, unit="pairs/s", cores=ref.threads, nproc=os.cpu_count(), kind=ref.kind,
+                sample=ref.describe(len(times), pairs * len(times), dt))
     print(json.dumps(dict(
         impl="reference", metric="EGNN fwd node-pairs/sec (dim=512 N=1024)", value=value, unit="pairs/s",
         n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=dt / len(times) * 1e3, higher_is_better=True,
         scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=w["label"], note="bounded sample per step, CPU"), cpu_baseline=res,
+        config=bench_config(world, w), cpu_baseline=base,
         e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
 def arm_eager(args):
-    """Optional: the UNMODIFIED reference on the GPU (PyTorch eager), if it was installed into
-    baseline/_ref (git-ignored).  This is the '>= 10x the reference's own GPU eager path' comparison
-    of BASELINE.json's north_star; not part of the driver's contract."""
-    ref = os.path.join(REPO, "baseline", "_ref")
-    if not os.path.isdir(os.path.join(ref, "egnn_pytorch")):
-        print(json.dumps(dict(impl="reference-gpu-eager", unavailable="baseline/_ref not installed")))
-        return
-    sys.path.insert(0, ref)
-    from egnn_pytorch import EGNN as RefEGNN
-    w = WORKLOADS[args.workload]
+    """Optional stand-alone run of the `gpu_eager_baseline` leg."""
     dev = torch.device("cuda", 0)
-    dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
-    torch.manual_seed(0)
-    mod = RefEGNN(**w["cfg"]).to(dtype).to(dev).eval()
-    g = torch.Generator().manual_seed(1)
-    feats = torch.randn(w["B"], w["N"], w["cfg"]["dim"], generator=g).to(dev, dtype)
-    coors = torch.randn(w["B"], w["N"], w["C"], generator=g).to(dev, dtype)
-    with torch.no_grad():
-        for _ in range(max(2, args.warmup)):
-            mod(feats, coors)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.steps):
-            mod(feats, coors)
-        b.record()
-        torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / args.steps
-    pairs = w["B"] * w["N"] * w["N"]
-    print(json.dumps(dict(impl="reference-gpu-eager", metric="EGNN fwd node-pairs/sec (dim=512 N=1024)",
-                          value=pairs / (ms * 1e-3), unit="pairs/s", ms_per_step=ms, dtype=args.dtype, steps=args.steps,
-                          peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
-                          config=dict(workload=w["label"]))))
+    print(json.dumps(dict(impl="reference-gpu-eager", **gpu_eager_baseline(args.workload, dev, float("nan")))))
 
 
 def main():
@@ -437,9 +601,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="metric, e2e and roofline only (profiling runs)")
     args = ap.parse_args()
     if args.impl == "cpu-sample":
-        print(json.dumps(cpu_baseline_sample(args.workload)[0]))
+        print(json.dumps(cpu_sample(args.workload)))
         return
     {"ours": arm_ours, "reference": arm_reference, "eager": arm_eager}[args.impl](args)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:

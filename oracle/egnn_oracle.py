@@ -235,6 +235,82 @@ def egnn_layer_forward(params, cfg, feats, coors, edges=None, mask=None, adj_mat
     return feats_out, coors_out
 
 
+# ----------------------------------------------------------------------------- edge-list mode
+
+
+def egnn_layer_forward_edge_list(params, cfg, feats, coors, neighbors, edges=None, mask=None, dtype=np.float64):
+    """The layer on a caller-supplied edge list -- message passing in the flat
+    per-edge form of the reference's PyG layer (`EGNN_Sparse.forward / message / propagate`,
+    egnn_pytorch_geometric.py:182-267: per-edge `edge_mlp(cat[x_i, x_j, edge_attr])`, per-edge coordinate
+    weight, `aggregate` = scatter-add onto the receiving node, `node_mlp(cat[norm(x), m_i]) + x`), written in the
+    DENSE layer's conventions so that it is the same function as `EGNN.forward` restricted to these edges:
+    edge-input column order [h_i | h_j | d | e_ij] (egnn_pytorch.py:282-285), rel = x_i - x_j (:232),
+    masks / clamp / CoorsNorm / pooling exactly as :292-333.
+
+    `neighbors` int [B,N,k]: neighbors[b,i,s] = j lists the edges j -> i; an entry < 0 is an empty slot and
+    contributes to nothing.  `valid_radius` does not apply (it is a property of the top-k ranking, :260).
+    Mean pooling: with a node mask the masked mean over existing, unmasked edges (:325-328, safe_div :13-16);
+    without one the reference's plain `.mean` over the k slots (:330).
+
+    Deliberately NOT the gather formulation of `egnn_layer_forward`: a flat list of E edges, one row per edge,
+    `np.add.at` for the aggregation -- an independent restatement to check the CUDA neighbour-list kernels."""
+    P = {k: np.asarray(v, dtype=dtype) for k, v in params.items()}
+    feats = np.asarray(feats, dtype=dtype)
+    coors = np.asarray(coors, dtype=dtype)
+    nb = np.asarray(neighbors).astype(np.int64)
+    b, n, d = feats.shape
+    k = nb.shape[-1]
+    assert nb.shape[:2] == (b, n) and (nb < n).all()
+    F = cfg["fourier_features"]
+    eb, ei, _ = np.nonzero(nb >= 0)                                  # one row per existing edge
+    ej = nb[nb >= 0]
+    x_i, x_j, h_i, h_j = coors[eb, ei], coors[eb, ej], feats[eb, ei], feats[eb, ej]
+    rel = x_i - x_j                                                  # geometric.py:196 in the dense sign convention (:232)
+    dist = (rel ** 2).sum(-1)                                        # geometric.py:197
+    dfeat = fourier_features_of(dist, F) if F > 0 else dist[:, None]  # geometric.py:199-201
+    parts = [h_i, h_j, dfeat]
+    if edges is not None:
+        parts.append(np.asarray(edges, dtype=dtype)[eb, ei, ej])
+    edge_in = np.concatenate(parts, axis=-1)
+    m = silu(linear(silu(linear(edge_in, P["edge_mlp.0.weight"], P["edge_mlp.0.bias"])),
+                    P["edge_mlp.3.weight"], P["edge_mlp.3.bias"]))   # message(), geometric.py:214-216
+    if cfg["soft_edges"]:
+        m = m * sigmoid(linear(m, P["edge_gate.0.weight"], P["edge_gate.0.bias"]))   # geometric.py:257-258
+    live = None
+    if mask is not None:
+        mk = np.asarray(mask).astype(bool)
+        live = mk[eb, ei] & mk[eb, ej]                               # egnn_pytorch.py:292-297
+    coors_out = coors.copy()
+    if cfg["update_coors"]:
+        w = linear(silu(linear(m, P["coors_mlp.0.weight"], P["coors_mlp.0.bias"])),
+                   P["coors_mlp.3.weight"], P["coors_mlp.3.bias"])[:, 0]            # geometric.py:238
+        if live is not None:
+            w = np.where(live, w, 0.0)                               # egnn_pytorch.py:309
+        cv = cfg["coor_weights_clamp_value"]
+        if cv is not None:
+            w = np.clip(w, -cv, cv)                                  # :313
+        rel_n = rel
+        if cfg["norm_coors"]:                                        # geometric.py:246, CoorsNorm
+            rel_n = rel / np.maximum(np.sqrt((rel ** 2).sum(-1, keepdims=True)), 1e-8) * P["coors_norm.scale"]
+        np.add.at(coors_out, (eb, ei), w[:, None] * rel_n)           # aggregate('add') + coors, geometric.py:248-249
+    feats_out = feats.copy()
+    if cfg["update_feats"]:
+        mm = m if live is None else np.where(live[:, None], m, 0.0)  # :322
+        m_i = np.zeros((b, n, m.shape[-1]), dtype=dtype)
+        np.add.at(m_i, (eb, ei), mm)                                 # aggregate, geometric.py:259
+        if cfg["m_pool_method"] == "mean":
+            if live is not None:
+                cnt = np.zeros((b, n, 1), dtype=dtype)
+                np.add.at(cnt, (eb, ei), live[:, None].astype(dtype))
+                m_i = np.where(cnt == 0, 0.0, m_i / np.maximum(cnt, 1e-8))
+            else:
+                m_i = m_i / k
+        normed = layer_norm(feats, P["node_norm.weight"], P["node_norm.bias"]) if cfg["norm_feats"] else feats
+        h1 = silu(linear(np.concatenate([normed, m_i], axis=-1), P["node_mlp.0.weight"], P["node_mlp.0.bias"]))
+        feats_out = linear(h1, P["node_mlp.3.weight"], P["node_mlp.3.bias"]) + feats   # geometric.py:261-263
+    return feats_out, coors_out
+
+
 # ----------------------------------------------------------------------------- the network
 
 

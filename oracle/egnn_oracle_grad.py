@@ -35,8 +35,11 @@ def _linear_bwd(gy, x, w):
     return gx, gw, gb
 
 
-def egnn_layer_backward(params, cfg, feats, coors, edges, mask, adj_mat, g_feats_out, g_coors_out):
+def egnn_layer_backward(params, cfg, feats, coors, edges, mask, adj_mat, g_feats_out, g_coors_out, neighbors=None):
     """Gradient of sum(feats_out * g_feats_out) + sum(coors_out * g_coors_out) of one layer.
+
+    `neighbors` int [B,N,k] (edge-list mode, see `egnn_oracle.egnn_layer_forward_edge_list`): these lists stand
+    in for the top-k result; entries < 0 are empty slots (their pair is masked out of every sum).
 
     Returns dict(feats [B,N,dim], coors [B,N,C], edges [B,N,N,e] | None, params {state-dict key: grad}).
     Neighbour selection (egnn_pytorch.py:237-260) is piecewise constant and contributes no gradient, exactly
@@ -56,7 +59,16 @@ def egnn_layer_backward(params, cfg, feats, coors, edges, mask, adj_mat, g_feats
     iidx = np.arange(n)[None, :, None]
 
     # ------------------------------------------------------------ forward, keeping intermediates
-    if use_nearest:
+    slot_ok = None
+    if neighbors is not None:
+        use_nearest = True
+        nb = np.asarray(neighbors).astype(np.int64)
+        slot_ok = nb >= 0
+        jidx = np.where(slot_ok, nb, np.broadcast_to(iidx, nb.shape))
+        nbhd_mask = np.ones(nb.shape, dtype=bool)
+        xj, hj = coors[bidx, jidx], feats[bidx, jidx]
+        eij = None if edges is None else edges[bidx, iidx, jidx]
+    elif use_nearest:
         jidx, nbhd_mask, _ = neighbour_selection(cfg, coors, mask, adj_mat)
         xj, hj = coors[bidx, jidx], feats[bidx, jidx]
         eij = None if edges is None else edges[bidx, iidx, jidx]
@@ -85,6 +97,9 @@ def egnn_layer_backward(params, cfg, feats, coors, edges, mask, adj_mat, g_feats
     pmask = None
     if mask is not None:
         pmask = (mask[:, :, None] & mask[bidx, jidx] & nbhd_mask) if use_nearest else (mask[:, :, None] & mask[:, None, :])
+    has_node_mask = pmask is not None
+    if slot_ok is not None:
+        pmask = slot_ok if pmask is None else (pmask & slot_ok)
 
     grads = {}
     g_m = np.zeros_like(m_ij)                                         # dL/dm_ij (after the gate)
@@ -95,7 +110,7 @@ def egnn_layer_backward(params, cfg, feats, coors, edges, mask, adj_mat, g_feats
     if cfg["update_feats"]:
         mm = m_ij if pmask is None else np.where(pmask[..., None], m_ij, 0.0)
         if cfg["m_pool_method"] == "mean":
-            if pmask is not None:
+            if has_node_mask:
                 cnt = pmask.sum(-1, keepdims=True).astype(f8)
                 inv = np.where(cnt == 0, 0.0, 1.0 / np.maximum(cnt, 1e-8))
             else:

@@ -14,7 +14,17 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [REPO, os.path.join(REPO, "tests")]
 from egnn_pytorch_b200 import EGNN, EGNN_Network  # noqa: E402
 
+ONLY = [t for t in os.environ.get("ONLY", "").split(",") if t]      # e.g. ONLY=c4 NOREF=1 for an ncu capture
+DTYPES = [t for t in os.environ.get("DTYPES", "bf16,fp32").split(",") if t]
+
+
+def want(tag):
+    return not ONLY or tag in ONLY
+
+
 try:
+    if os.environ.get("NOREF"):
+        raise ImportError
     sys.path.insert(0, os.path.join(REPO, "baseline", "_ref"))
     import egnn_pytorch as ref
 except Exception:  # pragma: no cover
@@ -83,28 +93,33 @@ R = ref.EGNN if ref else None
 RN = ref.EGNN_Network if ref else None
 
 # c1
-o, t = build(EGNN, R, dict(dim=512), torch.float32)
-run("c1 EGNN(512) B=1 N=16 fp32", o, t, (torch.randn(1, 16, 512, generator=g).to(dev), torch.randn(1, 16, 3, generator=g).to(dev)), {}, 256, None, 200, 50)
+if want("c1"):
+  o, t = build(EGNN, R, dict(dim=512), torch.float32)
+  run("c1 EGNN(512) B=1 N=16 fp32", o, t, (torch.randn(1, 16, 512, generator=g).to(dev), torch.randn(1, 16, 3, generator=g).to(dev)), {}, 256, None, 200, 50)
 # c2 bf16 and fp32
-for dt in (torch.bfloat16, torch.float32):
+for dt in [d for d in (torch.bfloat16, torch.float32) if want("c2") and str(d)[6:].replace("bfloat16", "bf16").replace("float32", "fp32") in DTYPES]:
     o, t = build(EGNN, R, dict(dim=512), dt)
     f, x = torch.randn(4, 1024, 512, generator=g).to(dev, dt), torch.randn(4, 1024, 3, generator=g).to(dev, dt)
     run(f"c2 EGNN(512) B=4 N=1024 {str(dt)[6:]}", o, t, (f, x), {}, 4 * 1024 * 1024, None, 20, 3)
 # c3
-o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.float32)
-f, x, m = torch.randint(0, 21, (1, 1024), generator=g).to(dev), torch.randn(1, 1024, 3, generator=g).to(dev), torch.ones(1, 1024, dtype=torch.bool, device=dev)
-run("c3 Network depth3 dim32 N=1024 k=8 fp32", o, t, (f, x), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
-o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.bfloat16)
-run("c3 Network depth3 dim32 N=1024 k=8 bf16", o, t, (f, x.bfloat16()), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
+if want("c3"):
+  f, x, m = torch.randint(0, 21, (1, 1024), generator=g).to(dev), torch.randn(1, 1024, 3, generator=g).to(dev), torch.ones(1, 1024, dtype=torch.bool, device=dev)
+  if "fp32" in DTYPES:
+    o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.float32)
+    run("c3 Network depth3 dim32 N=1024 k=8 fp32", o, t, (f, x), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
+  if "bf16" in DTYPES:
+    o, t = build(EGNN_Network, RN, dict(num_tokens=21, num_positions=1024, dim=32, depth=3, num_nearest_neighbors=8, coor_weights_clamp_value=2.0), torch.bfloat16)
+    run("c3 Network depth3 dim32 N=1024 k=8 bf16", o, t, (f, x.bfloat16()), dict(mask=m), 3 * 1024 * 1024, 3 * 1024 * 8, 100, 20)
 # c4 (8 graphs = one GPU's share of B=64)
-for dt in (torch.bfloat16, torch.float32):
+for dt in [d for d in (torch.bfloat16, torch.float32) if want("c4") and str(d)[6:].replace("bfloat16", "bf16").replace("float32", "fp32") in DTYPES]:
     o, t = build(EGNN, R, dict(dim=256, edge_dim=4, num_nearest_neighbors=32), dt)
     f, x = torch.randn(8, 4096, 256, generator=g).to(dev, dt), torch.randn(8, 4096, 3, generator=g).to(dev, dt)
     e = torch.randn(8, 4096, 4096, 4, generator=g).to(dev, dt)
     run(f"c4 EGNN(256,e4) k=32 N=4096 B=8/GPU {str(dt)[6:]}", o, t, (f, x, e), {}, 8 * 4096 * 4096, 8 * 4096 * 32, 10, 2)
     del e
 # c5
-o, t = build(EGNN_Network, RN, dict(num_tokens=21, dim=32, depth=3, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True), torch.float32)
 n = 8192
-f, x, m = torch.randint(0, 21, (1, n), generator=g).to(dev), torch.randn(1, n, 3, generator=g).to(dev), torch.ones(1, n, dtype=torch.bool, device=dev)
-run("c5 Network only_sparse adj3 N=8192 fp32", o, t, (f, x), dict(adj_mat=chain(n).to(dev), mask=m), 3 * n * n, 3 * n * 9, 10, 2)
+for dt in [d for d in (torch.float32, torch.bfloat16) if want("c5") and str(d)[6:].replace("bfloat16", "bf16").replace("float32", "fp32") in DTYPES]:
+    o, t = build(EGNN_Network, RN, dict(num_tokens=21, dim=32, depth=3, num_adj_degrees=3, adj_dim=8, only_sparse_neighbors=True), dt)
+    f, x, m = torch.randint(0, 21, (1, n), generator=g).to(dev), torch.randn(1, n, 3, generator=g).to(dev, dt), torch.ones(1, n, dtype=torch.bool, device=dev)
+    run(f"c5 Network only_sparse adj3 N=8192 {str(dt)[6:]}", o, t, (f, x), dict(adj_mat=chain(n).to(dev), mask=m), 3 * n * n, 3 * n * 9, 10, 2)

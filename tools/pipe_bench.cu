@@ -1,28 +1,35 @@
-// Micro-benchmark of the SM pipes the fused edge kernel leans on (MUFU.TANH / EX2, FFMA, HFMA2.BF16):
-// gives the measured denominators for the "sfu" roofline in bench.py / DESIGN.md.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_bench tools/pipe_bench.cu && ./pipe_bench
+// Micro-benchmark of the SM pipes the fused edge kernel leans on (MUFU.TANH / EX2, FFMA, FFMA2, HFMA2.BF16)
+// and of the kernel's own per-value instruction mix: gives the measured denominators for the "sfu"
+// roofline in bench.py / DESIGN.md and the ceiling of the round loop without any synchronisation.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/pipe_bench tools/pipe_bench.cu && ./tools/pipe_bench
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+
+__device__ __forceinline__ unsigned long long pk(float a, float b) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void upk(unsigned long long r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, int iters, float seed) {
   float v[8];
   uint32_t u[8];
+  unsigned long long q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { v[i] = seed + threadIdx.x * 1e-3f + i; u[i] = __float_as_uint(v[i]); }
+  for (int i = 0; i < 8; ++i) { v[i] = seed + threadIdx.x * 1e-3f + i; u[i] = __float_as_uint(v[i]); q[i] = pk(v[i], v[i] + 1.f); }
+  const unsigned long long one2 = pk(seed, seed);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (OP == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));
       if (OP == 1) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
-      if (OP == 2) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v[i]));
       if (OP == 3) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(u[i]));
       if (OP == 4) asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
       if (OP == 5) asm volatile("fma.rn.bf16x2 %0, %0, %1, %0;" : "+r"(u[i]) : "r"(0x3f803f80u));
-      if (OP == 7) { unsigned long long r = ((unsigned long long)u[i] << 32) | u[(i + 1) & 7];
-                     asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(r) : "l"(0x3f8000003f800000ull));
-                     u[i] = (uint32_t)(r >> 32); }
+      if (OP == 7) asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(q[i]) : "l"(one2));
+      if (OP == 8) asm volatile("min.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(seed));
+      if (OP == 9) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
       if (OP == 6) { asm volatile("tanh.approx.f32 %0, %0;" : "+f"(v[i]));            // mixed: 1 MUFU + 3 FMA
                      asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
                      asm volatile("fma.rn.f32 %0, %0, %1, %0;" : "+f"(v[i]) : "f"(seed));
@@ -31,37 +38,135 @@ __global__ void __launch_bounds__(1024) k(float* out, int iters, float seed) {
   }
   float s = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += v[i] + __uint_as_float(u[i]);
+  for (int i = 0; i < 8; ++i) { float a, b; upk(q[i], a, b); s += v[i] + __uint_as_float(u[i]) + a + b; }
   if (s == 12345.678f) out[0] = s;
 }
 
-template <int OP>
-void run(const char* name, double ops_per_inner, int sms) {
-  float* out; cudaMalloc(&out, 4);
-  const int iters = 4096, blocks = sms * 2;
-  k<OP><<<blocks, 1024>>>(out, 16, 1.0f);
+// NF2 packed FFMA2 (on 2 values) + NA alu ops per PAIR of tanh: how much FMA/ALU work rides along with a saturated MUFU pipe
+template <int NF2, int NA>
+__global__ void __launch_bounds__(512) kmix(float* out, int iters, float seed) {
+  unsigned long long q[8];
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { q[i] = pk(seed + threadIdx.x * 1e-3f + i, seed + i); u[i] = threadIdx.x + i; }
+  const unsigned long long c2 = pk(seed, seed);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a, b; upk(q[i], a, b);
+      asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a));
+      asm volatile("tanh.approx.f32 %0, %0;" : "+f"(b));
+      q[i] = pk(a, b);
+#pragma unroll
+      for (int f = 0; f < NF2; ++f) asm volatile("fma.rn.f32x2 %0, %0, %1, %0;" : "+l"(q[i]) : "l"(c2));
+#pragma unroll
+      for (int f = 0; f < NA; ++f) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(u[(i + 1) & 7]));
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { float a, b; upk(q[i], a, b); s += a + b + __uint_as_float(u[i]); }
+  if (s == 12345.678f) out[0] = s;
+}
+
+// The round loop's own mix per pair of values, and variants that isolate what each companion instruction costs:
+//   V=0  FFMA2 (wd*d + A'), 2x FHADD.BF16 (+B'), 2x tanh, FFMA2 (y + y*tanh y), F2FP pack        [the kernel's mix]
+//   V=1  same without the F2FP pack            V=2  FHADD replaced by plain FADD on fp32 B' (no unpack at all)
+//   V=3  B' unpacked on the ALU pipe (SHL / LOP3) and added with one FADD2 (add.f32x2)
+//   V=4  A'+B' pre-added:  y = wd*d + (A'+B') in ONE FFMA2 (what a per-(i,j)-tile precombined operand would allow)
+template <int V>
+__global__ void __launch_bounds__(512) kround(float* out, int iters, float seed) {
+  float2 av[8], wv[8]; uint32_t bb[8]; uint32_t acc = 0; float facc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { av[i] = make_float2(seed * i, seed + i); wv[i] = make_float2(0.01f * i, 0.02f); bb[i] = 0x3c003c00u + i + threadIdx.x; }
+  float d = seed;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      unsigned long long z; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(z) : "l"(pk(wv[i].x, wv[i].y)), "l"(pk(d, d)), "l"(pk(av[i].x, av[i].y)));
+      float z0, z1; upk(z, z0, z1);
+      float y0, y1;
+      if (V == 0 || V == 1) {
+        asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(y0) : "r"(bb[i]), "f"(z0));
+        asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(y1) : "r"(bb[i]), "f"(z1));
+      } else if (V == 2) {
+        asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(y0) : "f"(__uint_as_float(bb[i])), "f"(z0));
+        asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(y1) : "f"(__uint_as_float(bb[i])), "f"(z1));
+      } else if (V == 3) {
+        uint32_t lo, hi;
+        asm volatile("shl.b32 %0, %1, 16;" : "=r"(lo) : "r"(bb[i]));
+        asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(hi) : "r"(bb[i]));
+        unsigned long long y; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(y) : "l"(z), "l"(pk(__uint_as_float(lo), __uint_as_float(hi))));
+        upk(y, y0, y1);
+      } else { y0 = z0; y1 = z1; }
+      float t0, t1;
+      asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(y0));
+      asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(y1));
+      unsigned long long h; asm volatile("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(h) : "l"(pk(y0, y1)), "l"(pk(t0, t1)));
+      float h0, h1; upk(h, h0, h1);
+      if (V == 1) { facc += h0 + h1; }
+      else { uint32_t p; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(h1), "f"(h0)); acc ^= p; }
+    }
+    d += 1e-3f;
+  }
+  if (acc == 0x12345678u || facc == 1234.5f) out[0] = __uint_as_float(acc) + facc;
+}
+
+static double time_ms(void (*launch)(int), int iters) {
+  launch(16);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   cudaEventRecord(a);
-  k<OP><<<blocks, 1024>>>(out, iters, 1.0f);
+  launch(iters);
   cudaEventRecord(b); cudaEventSynchronize(b);
   float ms; cudaEventElapsedTime(&ms, a, b);
-  double total = (double)blocks * 1024 * iters * 8 * ops_per_inner;
-  double per_s = total / (ms * 1e-3);
-  printf("%-28s %8.3f ms  %10.2f Gop/s  = %6.2f op/clk/SM @1965MHz\n", name, ms, per_s / 1e9, per_s / sms / 1.965e9);
-  cudaFree(out);
+  return ms;
+}
+
+static float* g_out; static int g_sms;
+template <int OP> void launch_k(int iters) { k<OP><<<g_sms * 2, 1024>>>(g_out, iters, 1.0f); }
+template <int NF2, int NA> void launch_mix(int iters) { kmix<NF2, NA><<<g_sms * 4, 512>>>(g_out, iters, 1.0f); }
+template <int V> void launch_round(int iters) { kround<V><<<g_sms * 4, 512>>>(g_out, iters, 1.0f); }
+template <int NF2, int NA> void launch_mix1(int iters) {           // one 512-thread CTA per SM (4 warps / SMSP), as the fused kernel runs
+  cudaFuncSetAttribute(kmix<NF2, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  kmix<NF2, NA><<<g_sms, 512, 200 * 1024>>>(g_out, iters, 1.0f);
+}
+template <int V> void launch_round1(int iters) {
+  cudaFuncSetAttribute(kround<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  kround<V><<<g_sms, 512, 200 * 1024>>>(g_out, iters, 1.0f);
+}
+
+template <int OP> void run(const char* name, double ops_per_inner) {
+  const int iters = 4096;
+  double ms = time_ms(launch_k<OP>, iters);
+  double per_s = (double)g_sms * 2 * 1024 * iters * 8 * ops_per_inner / (ms * 1e-3);
+  printf("%-44s %8.3f ms  %10.2f Gop/s  = %6.2f op/clk/SM @1965MHz\n", name, ms, per_s / 1e9, per_s / g_sms / 1.965e9);
+}
+void report(const char* name, double ms, double tanh_total) {
+  double per_s = tanh_total / (ms * 1e-3);
+  printf("%-44s %8.3f ms  %10.2f Gtanh/s = %6.2f tanh/clk/SM @1965MHz\n", name, ms, per_s / 1e9, per_s / g_sms / 1.965e9);
 }
 
 int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-  int sms = p.multiProcessorCount;
-  printf("%s, %d SMs\n", p.name, sms);
-  run<0>("tanh.approx.f32", 1, sms);
-  run<1>("ex2.approx.f32", 1, sms);
-  run<2>("rcp.approx.f32", 1, sms);
-  run<3>("tanh.approx.bf16x2 (x2)", 2, sms);
-  run<4>("fma.f32", 1, sms);
-  run<5>("fma.bf16x2 (x2)", 2, sms);
-  run<6>("tanh.f32 + 3 fma (per tanh)", 1, sms);
-  run<7>("fma.f32x2 (x2, +2 int ops)", 2, sms);
+  g_sms = p.multiProcessorCount;
+  cudaMalloc(&g_out, 4);
+  printf("%s, %d SMs\n", p.name, g_sms);
+  run<0>("tanh.approx.f32", 1);
+  run<1>("ex2.approx.f32", 1);
+  run<3>("tanh.approx.bf16x2 (x2)", 2);
+  run<4>("fma.f32", 1);
+  run<5>("fma.bf16x2 (x2)", 2);
+  run<7>("fma.f32x2 (x2)", 2);
+  run<8>("min.f32", 1);
+  run<9>("add.s32", 1);
+  run<6>("tanh.f32 + 3 fma (per tanh)", 1);
+  const int it = 4096;
+#define MIX(NF, NA) report("2 tanh + " #NF " ffma2 + " #NA " alu, 16 warps/SMSP", time_ms(launch_mix<NF, NA>, it), (double)g_sms * 4 * 512 * it * 16); \
+                    report("2 tanh + " #NF " ffma2 + " #NA " alu,  4 warps/SMSP", time_ms(launch_mix1<NF, NA>, it), (double)g_sms * 512 * it * 16);
+  MIX(0, 0) MIX(2, 0) MIX(4, 0) MIX(6, 0) MIX(8, 0) MIX(10, 0) MIX(12, 0) MIX(4, 4) MIX(6, 4) MIX(8, 4) MIX(8, 8)
+#define RND(V, name) report(name " 16w", time_ms(launch_round<V>, it), (double)g_sms * 4 * 512 * it * 16); \
+                     report(name "  4w", time_ms(launch_round1<V>, it), (double)g_sms * 512 * it * 16);
+  RND(0, "round mix (ffma2,2 fhadd,2 tanh,ffma2,cvt)") RND(1, "round mix without the F2FP pack")
+  RND(2, "round mix, FADD instead of FHADD.BF16") RND(3, "round mix, ALU unpack + FADD2") RND(4, "round mix, A'+B' pre-added (no add)")
   return 0;
 }
