@@ -3,6 +3,8 @@
 //                             -> LayerNorm/concat -> node MLP (tcgen05 GEMM x2).
 // Option sets the tensor-core kernels do not cover return EGNN_ERR_UNSUPPORTED; the binding then runs
 // the fp32 SIMT kernels (never a CPU path).
+#include <stdlib.h>
+#include <mutex>
 #include "fast_path.h"
 #include "profile.h"
 #include "tc_gemm.cuh"
@@ -19,22 +21,31 @@ namespace {
 
 struct FastDims {
   Dims s;
-  int Hp;      // H rounded up to 64 (hidden chunks of the fused kernel)
+  int Hp;      // H rounded up to 16 (one K step of the fused kernels' MMA)
   int Kn;      // dim + m rounded up to 8 (K of the first node GEMM)
+  int L;       // one-hot label channels (num_labels when the layer has a label embedding)
+  int QT;      // per-pair scalar channels: d | sin | cos | continuous edges | one-hot labels
+  int QR;      // rows of the packed Wq table (>= 1 + TK_QE so that the neighbour-list kernel can view rows 1..4)
 };
 
 // layout of the packed-parameter buffer (byte offsets, 256-aligned)
 struct FastPack {
-  size_t w1i, w1j, b1, wdh, weh, w2p, epi, wn1, bn1, wn2, bn2, lng, lnb, total;
+  size_t w1i, w1j, b1, wq, w2p, epi, wn1, bn1, wn2, bn2, lng, lnb, total;
 };
 
 FastDims fast_dims(const EgnnLayerDesc& d) {
   FastDims f;
   f.s = make_dims(d);
-  f.Hp = round_up_i(f.s.H, 64);
+  f.Hp = round_up_i(f.s.H, 16);
   f.Kn = round_up_i(f.s.dim + f.s.m, 8);
+  f.L = d.label_dim > 0 ? d.num_labels : 0;
+  f.QT = 1 + 2 * d.fourier + d.edge_dim + f.L;
+  f.QR = f.QT > 1 + TK_QE ? f.QT : 1 + TK_QE;
   return f;
 }
+
+// the lean instantiation of the dense kernel covers 3-D coordinates with the distance as the only per-pair channel
+bool pair_is_lean(const FastDims& f) { return f.s.C == 3 && f.QT == 1; }
 
 FastPack fast_pack_layout(const FastDims& f) {
   FastPack p;
@@ -44,8 +55,7 @@ FastPack fast_pack_layout(const FastDims& f) {
   p.w1i = take((size_t)f.Hp * d * 2);
   p.w1j = take((size_t)f.Hp * d * 2);
   p.b1 = take((size_t)f.Hp * 4);
-  p.wdh = take((size_t)f.Hp * 4);
-  p.weh = take((size_t)TK_QE * f.Hp * 4);
+  p.wq = take((size_t)f.QR * f.Hp * 4);
   p.w2p = take((size_t)f.Hp * 32);
   p.epi = take((size_t)TP_EPI_FLOATS * 4);
   p.wn1 = take((size_t)2 * d * f.Kn * 2);
@@ -60,17 +70,19 @@ FastPack fast_pack_layout(const FastDims& f) {
 
 int fast_supported(const EgnnLayerDesc& d) {
   const FastDims f = fast_dims(d);
-  if (d.label_dim != 0 || d.fourier != 0) return EGNN_ERR_UNSUPPORTED;
-  if (d.k == 0) {                                                  // dense all-pairs: tc_pair_kernel
-    if (d.edge_dim != 0) return EGNN_ERR_UNSUPPORTED;
-    if (tc_pair_smem_bytes(f.Hp) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
+  if (d.m_dim != 16) return EGNN_ERR_UNSUPPORTED;                  // one 16-column accumulator per (row, warpgroup)
+  if (d.dim % 8 != 0) return EGNN_ERR_UNSUPPORTED;                 // 16-byte rows for cp.async
+  if (d.C < 1 || d.C > TP_CMAX) return EGNN_ERR_UNSUPPORTED;
+  if (d.k == 0) {                                                  // dense all-pairs: tc_pair_kernel<lean | generic>
+    if (f.QT > TP_QMAX) return EGNN_ERR_UNSUPPORTED;
+    const size_t smem = pair_is_lean(f) ? tc_pair_smem_bytes<false>(f.Hp, 1) : tc_pair_smem_bytes<true>(f.Hp, f.QT, 1 + 2 * f.s.F);
+    if (smem > 227 * 1024) return EGNN_ERR_UNSUPPORTED;
   } else {                                                         // neighbour lists: tc_knn_kernel
+    if (d.label_dim != 0 || d.fourier != 0 || d.C != 3) return EGNN_ERR_UNSUPPORTED;
     if (d.k > 32 || d.edge_dim > TK_QE) return EGNN_ERR_UNSUPPORTED;
     if (tc_knn_smem_bytes(f.Hp, d.edge_dim > 0) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
+    if (!(f.s.row0 == 0 && f.s.row1 == d.N)) return EGNN_ERR_UNSUPPORTED;
   }
-  if (d.C != 3 || d.m_dim != 16) return EGNN_ERR_UNSUPPORTED;
-  if (d.dim % 8 != 0) return EGNN_ERR_UNSUPPORTED;                 // 16-byte rows for cp.async
-  if (!(d.row_begin == 0 && (d.row_end == 0 || d.row_end == d.N))) return EGNN_ERR_UNSUPPORTED;
   return EGNN_OK;
 }
 
@@ -89,16 +101,28 @@ __global__ void fast_pack_kernel(FastDims f, FastPack L, EgnnLayerWeights w, uin
     w1j[x] = c < H ? static_cast<const __nv_bfloat16*>(w.edge_w1)[(size_t)c * E + d + k] : z;
   }
   float* b1 = reinterpret_cast<float*>(out + L.b1);
-  float* wdh = reinterpret_cast<float*>(out + L.wdh);
-  for (size_t c = t0; c < (size_t)Hp; c += stride) {
-    b1[c] = c < (size_t)H ? bf(w.edge_b1, c) : 0.f;
-    wdh[c] = c < (size_t)H ? 0.5f * bf(w.edge_w1, c * E + 2 * d) : 0.f;      // the d_ij column of W1, pre-halved
-  }
-  float* weh = reinterpret_cast<float*>(out + L.weh);                          // continuous edge columns, pre-halved
-  for (size_t x = t0; x < (size_t)TK_QE * Hp; x += stride) {
+  for (size_t c = t0; c < (size_t)Hp; c += stride) b1[c] = c < (size_t)H ? bf(w.edge_b1, c) : 0.f;
+  // Per-pair scalar columns of W1, pre-halved, in the kernels' channel order:
+  //   row 0: d_ij (W1 column 2d + 2F, the LAST of the fourier block, egnn_pytorch.py:34-41) | rows 1..F: sin(d / 2^k)
+  //   | rows F+1..2F: cos(d / 2^k) | edge_dim rows: continuous edge channels | L rows: label table
+  //   Tab[l] = label_emb[l] @ W1[:, label columns]^T  (the embedding of :430-432 folded through Linear-1).
+  float* wq = reinterpret_cast<float*>(out + L.wq);
+  const int F = s.F, ed = s.edge_dim, ld = s.label_dim;
+  for (size_t x = t0; x < (size_t)f.QR * Hp; x += stride) {
     const int q = (int)(x / Hp);
     const size_t c = x % Hp;
-    weh[x] = (c < (size_t)H && q < s.edge_dim) ? 0.5f * bf(w.edge_w1, c * E + 2 * d + 1 + q) : 0.f;
+    float v = 0.f;
+    if (c < (size_t)H) {
+      const size_t row = c * E + 2 * d;
+      if (q == 0) v = bf(w.edge_w1, row + 2 * F);
+      else if (q <= 2 * F) v = bf(w.edge_w1, row + (q - 1));
+      else if (q < 1 + 2 * F + ed) v = bf(w.edge_w1, row + 2 * F + 1 + (q - 1 - 2 * F));
+      else if (q < 1 + 2 * F + ed + f.L) {
+        const int l = q - 1 - 2 * F - ed;
+        for (int t = 0; t < ld; ++t) v += bf(w.label_emb, (size_t)l * ld + t) * bf(w.edge_w1, row + 2 * F + 1 + ed + t);
+      }
+    }
+    wq[x] = 0.5f * v;
   }
   // W2 [16][H] -> UMMA K-major core matrices: [slab = c/16][kc = (c%16)/8][nc = n/8][r = n%8][e = c%8]
   __nv_bfloat16* w2p = reinterpret_cast<__nv_bfloat16*>(out + L.w2p);
@@ -186,14 +210,51 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   return w;
 }
 
-int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
-  static bool attr_set[64] = {false};
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device), under a mutex: the only mutable
+// state of this file, written once per device and never shrunk.  TAG distinguishes kernels of identical type.
+template <int TAG, typename K>
+int ensure_dyn_smem(K kernel, size_t bytes) {
+  static std::mutex mu;
+  static size_t set[64] = {0};
   int dev = 0;
   EGNN_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 64 && !attr_set[dev]) {
-    EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    attr_set[dev] = true;
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 64 || set[dev] < bytes) {
+    EGNN_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev < 64) set[dev] = bytes;
   }
+  return EGNN_OK;
+}
+
+int sm_count(int* out) {
+  static std::mutex mu;
+  static int cached[64] = {0};
+  int dev = 0;
+  EGNN_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && cached[dev] > 0) { *out = cached[dev]; return EGNN_OK; }
+  int n = 0;
+  EGNN_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) cached[dev] = n;
+  *out = n;
+  return EGNN_OK;
+}
+
+// Optional start-up delay between the warpgroups of the persistent dense kernel (tc_pair.cuh), EGNN_B200_SKEW_NS.
+// Default 0: measured on B200 (profiles/r02_tc_pair_skew_sweep.txt) de-phasing the warpgroups' epilogues buys nothing --
+// the kernel is bound by per-warp latency (1/2/3/4 warps per sub-partition reach 0.28/0.47/0.58/0.67 of the MUFU
+// roofline), not by the pipe idling during the epilogues.
+uint32_t pair_skew_ns() {
+  static const uint32_t v = [] {
+    const char* e = getenv("EGNN_B200_SKEW_NS");
+    return e ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
+  }();
+  return v;
+}
+
+int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
+  if (g.M <= 0) return EGNN_OK;
+  EGNN_TRY((ensure_dyn_smem<0>(tc_gemm_kernel, GEMM_SMEM_BYTES)));
   dim3 grid(ceil_div(g.Nout, GEMM_BN), ceil_div(g.M, GEMM_BM));
   tc_gemm_kernel<<<grid, 128, GEMM_SMEM_BYTES, st>>>(g);
   EGNN_LAUNCH_CHECK();
@@ -254,43 +315,68 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
   const __nv_bfloat16* feats = static_cast<const __nv_bfloat16*>(io.feats);
   const bool uf = d.flags & EGNN_FLAG_UPDATE_FEATS, uc = d.flags & EGNN_FLAG_UPDATE_COORS;
 
+  // Row range (row-sharded single graph): the j side (B') always covers all nodes, the i side
+  // (A', the fused kernel's row groups, the node update) only rows [row0, row1) of every graph.
+  const int r0 = s.row0, r1 = s.row1, R = r1 - r0;
+  const bool all_rows = (r0 == 0 && r1 == s.N);
+  const int nseg = all_rows ? 1 : s.B;                        // contiguous row segments for the per-node GEMMs
+  auto seg_begin = [&](int sg) { return all_rows ? (size_t)0 : (size_t)sg * s.N + r0; };
+  const int seg_rows = all_rows ? s.M : R;
+
   {  // per-node tables, pre-halved for the tanh form of SiLU:  A' = 0.5 (h W1_i^T + b1),  B' = 0.5 h W1_j^T
     StageTimer tm(st, STAGE_NODE_PRE);
     TcGemmArgs g{};
-    g.A = feats; g.lda = s.dim; g.K = s.dim; g.M = s.M; g.Nv = f.Hp; g.Nout = f.Hp; g.scale = 0.5f; g.act = 0;
+    g.lda = s.dim; g.K = s.dim; g.Nv = f.Hp; g.Nout = f.Hp; g.scale = 0.5f; g.act = 0; g.R = nullptr; g.ldr = 0; g.ldo = f.Hp;
     g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1i); g.ldw = s.dim;
-    g.bias = reinterpret_cast<const float*>(pk + L.b1); g.R = nullptr; g.ldr = 0;
-    g.out = Atab; g.ldo = f.Hp; g.out_f32 = 1;
-    EGNN_TRY(launch_tc_gemm(g, st));
+    g.bias = reinterpret_cast<const float*>(pk + L.b1);
+    g.out_f32 = 1;
+    for (int sg = 0; sg < nseg; ++sg) {
+      g.A = feats + seg_begin(sg) * s.dim; g.M = seg_rows; g.out = Atab + seg_begin(sg) * f.Hp;
+      EGNN_TRY(launch_tc_gemm(g, st));
+    }
+    g.A = feats; g.M = s.M;
     g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j); g.bias = nullptr;
     g.out = Btab; g.out_f32 = 0;
     EGNN_TRY(launch_tc_gemm(g, st));
   }
-  if (s.k == 0) {  // fused edge kernel, dense all-pairs
+  if (s.k == 0) {  // fused edge kernel, dense all-pairs (persistent: one CTA per SM walks the row groups)
     StageTimer tm(st, STAGE_PAIR);
     TcPairArgs a{};
-    a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim;
+    a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn;
+    a.C = s.C; a.Q = f.QT; a.F = s.F; a.edge_dim = s.edge_dim; a.num_labels = f.L;
+    a.row0 = r0; a.row1 = r1;
     a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp;
+    a.skew_ns = pair_skew_ns();
     a.Atab = Atab; a.Btab = Btab;
-    a.wdh = reinterpret_cast<const float*>(pk + L.wdh);
+    a.wq = reinterpret_cast<const float*>(pk + L.wq);
     a.w2p = reinterpret_cast<const __nv_bfloat16*>(pk + L.w2p);
     a.epi = reinterpret_cast<const float*>(pk + L.epi);
     a.coors = static_cast<const float*>(io.coors);
+    a.edges = static_cast<const __nv_bfloat16*>(io.edges);
+    a.labels = f.L > 0 ? io.edge_labels : nullptr;
     a.mask = io.mask;
     a.m_out = uf ? node_in + s.dim : nullptr;
     a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
-    const size_t smem = tc_pair_smem_bytes(f.Hp);
-    static size_t smem_set[64] = {0};
-    int dev = 0;
-    EGNN_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 64 && smem_set[dev] < smem) {
-      EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[dev] = smem;
+    if (f.L > 0 && !io.edge_labels) return EGNN_ERR_NULL;
+    if (s.edge_dim > 0 && !io.edges) return EGNN_ERR_NULL;
+    int sms = 0;
+    EGNN_TRY(sm_count(&sms));
+    const int items = s.B * ceil_div(R, TP_TI);
+    if (items > 0) {
+      const int grid = items < sms ? items : sms;
+      if (items < 2 * sms) a.skew_ns = 0;                      // too few row groups per CTA for the de-phasing to pay
+      if (pair_is_lean(f)) {
+        const size_t smem = tc_pair_smem_bytes<false>(f.Hp, 1);
+        EGNN_TRY((ensure_dyn_smem<1>(tc_pair_kernel<false>, smem)));
+        tc_pair_kernel<false><<<grid, TP_THREADS, smem, st>>>(a);
+      } else {
+        const size_t smem = tc_pair_smem_bytes<true>(f.Hp, f.QT, 1 + 2 * f.s.F);
+        EGNN_TRY((ensure_dyn_smem<2>(tc_pair_kernel<true>, smem)));
+        tc_pair_kernel<true><<<grid, TP_THREADS, smem, st>>>(a);
+      }
+      EGNN_LAUNCH_CHECK();
+      count_launch();
     }
-    dim3 grid(ceil_div(s.N, TP_TI), s.B);
-    tc_pair_kernel<<<grid, TP_THREADS, smem, st>>>(a);
-    EGNN_LAUNCH_CHECK();
-    count_launch();
   } else {         // neighbour lists: distance + top-k select, then the gathered fused edge kernel
     int32_t* nbr_idx = reinterpret_cast<int32_t*>(base + wl.nbr_idx);
     uint8_t* nbr_ok = base + wl.nbr_ok;
@@ -309,8 +395,8 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim; a.k = s.k; a.edge_dim = s.edge_dim;
     a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp;
     a.Atab = Atab; a.Btab = Btab;
-    a.wdh = reinterpret_cast<const float*>(pk + L.wdh);
-    a.weh = reinterpret_cast<const float*>(pk + L.weh);
+    a.wdh = reinterpret_cast<const float*>(pk + L.wq);                       // row 0 of the Wq table (no fourier here)
+    a.weh = reinterpret_cast<const float*>(pk + L.wq) + f.Hp;                // rows 1..4: edge channels (zero beyond edge_dim)
     a.w2p = reinterpret_cast<const __nv_bfloat16*>(pk + L.w2p);
     a.epi = reinterpret_cast<const float*>(pk + L.epi);
     a.coors = static_cast<const float*>(io.coors);
@@ -321,14 +407,8 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
     const bool ed = s.edge_dim > 0;
     const size_t smem = tc_knn_smem_bytes(f.Hp, ed);
-    static size_t smem_set[2][64] = {{0}};
-    int dev = 0;
-    EGNN_CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 64 && smem_set[ed][dev] < smem) {
-      if (ed) EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_knn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      else EGNN_CUDA_TRY(cudaFuncSetAttribute(tc_knn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set[ed][dev] = smem;
-    }
+    if (ed) EGNN_TRY((ensure_dyn_smem<3>(tc_knn_kernel<true>, smem)));
+    else EGNN_TRY((ensure_dyn_smem<4>(tc_knn_kernel<false>, smem)));
     dim3 grid(ceil_div(s.N, TK_ROWS), s.B);
     if (ed) tc_knn_kernel<true><<<grid, TK_THREADS, smem, st>>>(a);
     else tc_knn_kernel<false><<<grid, TK_THREADS, smem, st>>>(a);
@@ -336,29 +416,38 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     count_launch();
   }
   StageTimer post(st, STAGE_NODE_POST);
+  __nv_bfloat16* fout = static_cast<__nv_bfloat16*>(io.feats_out);
   if (uf) {  // h' = node_mlp([LN(h) | m_i]) + h
-    ln_concat_bf16_kernel<<<ceil_div(s.M * 32, 256), 256, 0, st>>>(
-        feats, reinterpret_cast<const float*>(pk + L.lng), reinterpret_cast<const float*>(pk + L.lnb), node_in, f.Kn,
-        s.dim, s.m, s.M, (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0);
-    EGNN_LAUNCH_CHECK();
-    count_launch();
-    TcGemmArgs g{};
-    g.A = node_in; g.lda = f.Kn; g.K = f.Kn; g.M = s.M; g.Nv = 2 * s.dim; g.Nout = 2 * s.dim; g.scale = 1.f; g.act = 1;
-    g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn1); g.ldw = f.Kn;
-    g.bias = reinterpret_cast<const float*>(pk + L.bn1);
-    g.out = h1; g.ldo = 2 * s.dim; g.out_f32 = 0;
-    EGNN_TRY(launch_tc_gemm(g, st));
-    g.A = h1; g.lda = 2 * s.dim; g.K = 2 * s.dim; g.Nv = s.dim; g.Nout = s.dim; g.act = 0;
-    g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn2); g.ldw = 2 * s.dim;
-    g.bias = reinterpret_cast<const float*>(pk + L.bn2);
-    g.R = feats; g.ldr = s.dim;
-    g.out = io.feats_out; g.ldo = s.dim; g.out_f32 = 0;
-    EGNN_TRY(launch_tc_gemm(g, st));
+    for (int sg = 0; sg < nseg; ++sg) {
+      const size_t o = seg_begin(sg);
+      ln_concat_bf16_kernel<<<ceil_div(seg_rows * 32, 256), 256, 0, st>>>(
+          feats + o * s.dim, reinterpret_cast<const float*>(pk + L.lng), reinterpret_cast<const float*>(pk + L.lnb),
+          node_in + o * f.Kn, f.Kn, s.dim, s.m, seg_rows, (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0);
+      EGNN_LAUNCH_CHECK();
+      count_launch();
+      TcGemmArgs g{};
+      g.A = node_in + o * f.Kn; g.lda = f.Kn; g.K = f.Kn; g.M = seg_rows; g.Nv = 2 * s.dim; g.Nout = 2 * s.dim; g.scale = 1.f; g.act = 1;
+      g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn1); g.ldw = f.Kn;
+      g.bias = reinterpret_cast<const float*>(pk + L.bn1);
+      g.out = h1 + o * 2 * s.dim; g.ldo = 2 * s.dim; g.out_f32 = 0;
+      EGNN_TRY(launch_tc_gemm(g, st));
+      g.A = h1 + o * 2 * s.dim; g.lda = 2 * s.dim; g.K = 2 * s.dim; g.Nv = s.dim; g.Nout = s.dim; g.act = 0;
+      g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn2); g.ldw = 2 * s.dim;
+      g.bias = reinterpret_cast<const float*>(pk + L.bn2);
+      g.R = feats + o * s.dim; g.ldr = s.dim;
+      g.out = fout + o * s.dim; g.ldo = s.dim; g.out_f32 = 0;
+      EGNN_TRY(launch_tc_gemm(g, st));
+    }
   } else if (io.feats_out != io.feats) {
-    EGNN_CUDA_TRY(cudaMemcpyAsync(io.feats_out, io.feats, (size_t)s.M * s.dim * 2, cudaMemcpyDeviceToDevice, st));
+    for (int sg = 0; sg < nseg; ++sg)
+      EGNN_CUDA_TRY(cudaMemcpyAsync(fout + seg_begin(sg) * s.dim, feats + seg_begin(sg) * s.dim, (size_t)seg_rows * s.dim * 2,
+                                    cudaMemcpyDeviceToDevice, st));
   }
   if (!uc && io.coors_out != io.coors)
-    EGNN_CUDA_TRY(cudaMemcpyAsync(io.coors_out, io.coors, (size_t)s.M * 3 * 4, cudaMemcpyDeviceToDevice, st));
+    for (int sg = 0; sg < nseg; ++sg)
+      EGNN_CUDA_TRY(cudaMemcpyAsync(static_cast<float*>(io.coors_out) + seg_begin(sg) * s.C,
+                                    static_cast<const float*>(io.coors) + seg_begin(sg) * s.C, (size_t)seg_rows * s.C * 4,
+                                    cudaMemcpyDeviceToDevice, st));
   return EGNN_OK;
 }
 

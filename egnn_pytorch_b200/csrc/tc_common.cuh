@@ -173,6 +173,8 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t saddr, const void* gptr, u
                : "memory");
 }
 
+template <int V> struct IntC { static constexpr int value = V; };     // compile-time int tag for generic lambdas
+
 // ------------------------------------------------------------------ scalar helpers
 // Packed fp32x2 FMA (Blackwell FFMA2): two independent a*b+c in one issue slot.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, i0 = blockIdx.x * TK_ROWS;
   const int rows_valid = min(TK_ROWS, N - i0);
-  const int nchunks = Hp / TK_KC;
+  const int nchunks = (Hp + TK_KC - 1) / TK_KC;
+  const int nsl_last = (Hp - (nchunks - 1) * TK_KC) / 16;        // valid K slabs of the last chunk (Hp is a multiple of 16)
   const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
 
   if (tid == 0) {
@@ -155,10 +156,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
 
   tc::mbar_wait(ldbar, 0);
   uint2 Bc[4][4];
+  {
+    const int nsl0 = nchunks == 1 ? nsl_last : 4;
 #pragma unroll
-  for (int rho = 0; rho < 4; ++rho)
+    for (int rho = 0; rho < 4; ++rho)
 #pragma unroll
-    for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = __ldg(Bp[rho] + sl * 4);
+      for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = sl < nsl0 ? __ldg(Bp[rho] + sl * 4) : make_uint2(0u, 0u);
+  }
 
   int pend_c = -1;
   auto issue_pending = [&]() {
@@ -171,10 +175,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     tc::tc_fence_after();
     if (lane == 0) {
       const uint32_t tm_g = tmem + g * TK_WGCOLS;
+      const int nk = pc + 1 == nchunks ? nsl_last : 4;
 #pragma unroll
       for (int kk = 0; kk < TK_KC / 16; ++kk) {
-        const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(pc * 4 + kk) * 512, 256u, 128u);
-        tc::mma_ts(tm_g, tm_g + 16 + pslot * 32 + kk * 8, bd, IDESC, (pc > 0 || kk > 0) ? 1u : 0u);
+        if (kk < nk) {
+          const uint64_t bd = tc::smem_desc_kmajor_noswizzle(w2a + (uint32_t)(pc * 4 + kk) * 512, 256u, 128u);
+          tc::mma_ts(tm_g, tm_g + 16 + pslot * 32 + kk * 8, bd, IDESC, (pc > 0 || kk > 0) ? 1u : 0u);
+        }
       }
       tc::mma_commit(&empty[g * TK_SLOTS + pslot]);
       if (pc + 1 == nchunks) tc::mma_commit(&accdone[g]);
@@ -188,17 +195,20 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     const uint32_t slot = (uint32_t)c % TK_SLOTS;
     const uint32_t ta = tm_wg + 16 + slot * 32;
     const bool more = c + 1 < nchunks;
+    const int nsl = c + 1 == nchunks ? nsl_last : 4, nsl_next = c + 2 == nchunks ? nsl_last : 4;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t hp[16];
 #pragma unroll
       for (int sl = 0; sl < 4; ++sl) {
-        const float4 av = *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16);
-        const float4 wv = *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4);
+        const bool slv = sl < nsl;                          // slabs beyond Hp (last chunk only): zeros, never multiplied
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 av = slv ? *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16) : zero4;
+        const float4 wv = slv ? *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4) : zero4;
         float4 we[TK_QE];
         if (EDGES) {
 #pragma unroll
-          for (int q = 0; q < TK_QE; ++q) we[q] = *reinterpret_cast<const float4*>(wes + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
+          for (int q = 0; q < TK_QE; ++q) we[q] = slv ? *reinterpret_cast<const float4*>(wes + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4) : zero4;
         }
 #pragma unroll
         for (int r2 = 0; r2 < 2; ++r2) {
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
           const float y2 = tc::add_bf16_lo(bb.y, z2), y3 = tc::add_bf16_hi(bb.y, z3);
           hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
           hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
-          if (more) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
+          if (more && sl < nsl_next) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
         }
       }
       if (half == 0) {

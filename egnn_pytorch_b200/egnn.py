@@ -28,6 +28,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import warnings
 
 import torch
 from torch import nn
@@ -194,6 +195,7 @@ class EGNN(nn.Module):
         self.init_eps = init_eps
         self.precision = precision
         self.last_path = None          # 'fp64-simt' | 'fp32-simt' | 'bf16-tcgen05' of the last call
+        self.cache_policy = "version"  # 'version' | 'always' -- see invalidate_cache()
         self._stage = {}
         self._tc_unsupported = set()
         self._call_cache = {}
@@ -219,12 +221,25 @@ class EGNN(nn.Module):
         self.__dict__["_fields_cache"] = cache
         return cache
 
+    def invalidate_cache(self):
+        """Drop every staged / packed copy of the parameters (they are rebuilt on the next call).
+
+        The caches are keyed on (storage pointer, tensor version) of each parameter.  Writes that go THROUGH
+        `.data` (`p.data.copy_(master)`, the master->model copy of apex / DeepSpeed / Megatron-style mixed
+        precision, some EMA loops) do not bump the version counter, so after such a write call this method -- or
+        set `cache_policy = "always"` to re-stage and re-pack on every forward (one small kernel per layer).
+        In training mode (`module.training` with a parameter that requires grad) the layer always re-packs."""
+        self._stage = {}
+        self._call_cache = {}
+        self.__dict__.pop("_fields_cache", None)
+
     def _staged(self, device, dtype):
         fields = self._state_fields()
         sig = tuple((p.data_ptr(), p._version) for _, _, _, p in fields)
         key = (device, dtype)
         st = self._stage.get(key)
-        if st is None or st["sig"] != sig:
+        always = self.cache_policy == "always" or (self.training and any(p.requires_grad for _, _, _, p in fields))
+        if st is None or st["sig"] != sig or always:
             with torch.no_grad():
                 tensors = {f: p.detach().to(device=device, dtype=dtype).contiguous() for _, _, f, p in fields}
             st = dict(sig=sig, tensors=tensors, packed={}, wstruct={})
@@ -333,6 +348,10 @@ class EGNN(nn.Module):
                 raise
         # the tensor-core kernels do not cover this option set: fp32 SIMT kernels (still on the GPU); remembered
         self._tc_unsupported.add(cfg_key)
+        warnings.warn(f"egnn_pytorch_b200: the bf16 tensor-core kernels do not cover this configuration (C={c}, k={k}, "
+                      f"edge_dim={cont_edge_dim}, label_dim={label_dim}, m_dim={self.m_dim}, fourier={self.fourier_features}); "
+                      f"running the fp32 SIMT kernels instead (about 5x slower, same results to fp32 accuracy)", UserWarning,
+                      stacklevel=3)
         return self._run(lib, dev, torch.float32, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
                          b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
 
@@ -351,7 +370,8 @@ class EGNN(nn.Module):
                 st["packed"] = {}
             T["label_emb"] = lab_w
 
-        ckey = (kdt, b, n, c, k, flags, cont_edge_dim, label_dim, 0 if label_emb is None else label_emb.shape[0], rows)
+        ckey = (kdt, b, n, c, k, flags, cont_edge_dim, label_dim, 0 if label_emb is None else label_emb.shape[0], rows,
+                float(self.valid_radius), float(self.coor_weights_clamp_value or 0.0))
         cc = self._call_cache.get(ckey)
         if cc is None:
             desc = nat.LayerDesc(

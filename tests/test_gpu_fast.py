@@ -2,9 +2,9 @@
 
 Inputs and parameters are rounded to bf16 first, so the comparison isolates the kernels' internal
 rounding (bf16 B' table, bf16 hidden operand, bf16 m_i / h1, tanh.approx) from input quantisation.
-Stated tolerance: max|err| <= 3e-2 * max|reference output| for feats and <= 3e-2 * max|coordinate
-update| + 1e-3 for coors; the reference itself run in bf16 deviates from its fp32 self by 1.6e-2 / 4.7e-2
-at default init and 0.10 / 0.52 with Xavier weights."""
+Stated tolerance: max|err| <= 1e-2 * max|reference output| for feats and <= 1e-2 * max(max|coordinate
+update|, 1) for coors (measured 2e-3 .. 7e-3 of the respective scale); the reference itself run in bf16 deviates from its fp32 self by
+1.6e-2 / 4.7e-2 at default init and 0.10 / 0.52 with Xavier weights."""
 import numpy as np
 import pytest
 import torch
@@ -29,6 +29,25 @@ FAST_SPECS = {
     "d512_n256":       dict(kind=L, cfg=dict(dim=512), B=1, N=256, seed=91, init="xavier"),
     "d64_no_coors":    dict(kind=L, cfg=dict(dim=64, update_coors=False), B=1, N=40, seed=90, init="xavier"),
     "d64_no_feats":    dict(kind=L, cfg=dict(dim=64, update_feats=False), B=1, N=40, seed=89, init="xavier"),
+    # --- the generic instantiation of the dense kernel: dense edge channels (the reference's own test shape,
+    #     tests/test_equivariance.py:13-30), fourier features, other coordinate dimensions (:40), hidden widths
+    #     whose last chunk has 1..3 K slabs, degree labels through EGNN_Network
+    "d512_edges4":     dict(kind=L, cfg=dict(dim=512, edge_dim=4), B=1, N=16, seed=70, mask="padded"),
+    "d64_edges4":      dict(kind=L, cfg=dict(dim=64, edge_dim=4), B=2, N=140, seed=71, init="xavier", mask="padded"),
+    "d64_edges2_soft": dict(kind=L, cfg=dict(dim=64, edge_dim=2, soft_edges=True, norm_coors=True, m_pool_method="mean"), B=2, N=70,
+                            seed=72, init="xavier", mask="random"),
+    "d32_fourier2":    dict(kind=L, cfg=dict(dim=32, fourier_features=2), B=2, N=90, seed=73, init="xavier"),
+    "d64_fourier_e1":  dict(kind=L, cfg=dict(dim=64, fourier_features=3, edge_dim=1, coor_weights_clamp_value=0.7), B=1, N=130, seed=74,
+                            init="xavier", mask="padded"),
+    "d64_c5":          dict(kind=L, cfg=dict(dim=64), B=2, N=50, C=5, seed=75, init="xavier"),
+    "d64_c2_edges":    dict(kind=L, cfg=dict(dim=64, edge_dim=3, norm_coors=True), B=1, N=33, C=2, seed=76, init="xavier", mask="padded"),
+    "d40_tail":        dict(kind=L, cfg=dict(dim=40), B=2, N=130, seed=77, init="xavier"),            # H = 162 -> 176: last chunk 3 slabs
+    "d48_tail_e1":     dict(kind=L, cfg=dict(dim=48, edge_dim=1), B=1, N=520, seed=78, init="xavier"),  # 2 tiles per warpgroup, 5 j-tiles
+    "d64_many_rows":   dict(kind=L, cfg=dict(dim=64), B=3, N=700, seed=79, init="xavier", mask="padded"),   # > 2 row groups per CTA: ring reuse
+    "net_dense_adj":   dict(kind="network", cfg=dict(depth=2, dim=32, num_tokens=11, num_adj_degrees=2, adj_dim=4), B=2, N=40, seed=69,
+                            init="xavier", adj="chain", mask="padded"),
+    "net_dense_adj_e": dict(kind="network", cfg=dict(depth=2, dim=32, num_tokens=11, num_edge_tokens=5, edge_dim=3, num_adj_degrees=3,
+                                                     adj_dim=2), B=1, N=30, seed=68, init="xavier", adj="chain", edges=True),
     # --- neighbour lists on the tensor-core path (tc_knn_kernel)
     "knn_d64_k8":      dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=8), B=2, N=200, seed=80, init="xavier"),
     "knn_d64_k32_e4":  dict(kind=L, cfg=dict(dim=64, edge_dim=4, num_nearest_neighbors=32), B=2, N=100, seed=81, init="xavier",
@@ -54,9 +73,10 @@ def bf16_round(a):
 def run_fast(spec):
     case = cases.build_case(spec)
     case["params"] = {k: bf16_round(v) for k, v in case["params"].items()}
-    case["inputs"]["feats"] = bf16_round(case["inputs"]["feats"])
+    if np.issubdtype(np.asarray(case["inputs"]["feats"]).dtype, np.floating):      # token ids stay integers
+        case["inputs"]["feats"] = bf16_round(case["inputs"]["feats"])
     case["inputs"]["coors"] = bf16_round(case["inputs"]["coors"])      # a bf16 module is fed bf16 coordinates
-    if "edges" in case["inputs"]:
+    if case["inputs"].get("edges") is not None and np.issubdtype(np.asarray(case["inputs"]["edges"]).dtype, np.floating):
         case["inputs"]["edges"] = bf16_round(case["inputs"]["edges"])
     mod = util.make_module(case, torch.bfloat16)
     out = util.run_module(mod, case, torch.bfloat16)
@@ -67,7 +87,8 @@ def run_fast(spec):
 @pytest.mark.parametrize("name", list(FAST_SPECS))
 def test_fast_path_matches_oracle(name):
     case, mod, out = run_fast(FAST_SPECS[name])
-    assert mod.last_path == "bf16-tcgen05"
+    layers = [l[1] for l in mod.layers] if hasattr(mod, "layers") else [mod]
+    assert all(l.last_path == "bf16-tcgen05" for l in layers)
     assert out[0].dtype == torch.bfloat16
     want = cases.run_oracle(case)
     f_scale = max(1e-3, float(np.abs(want[0]).max()))
@@ -75,15 +96,33 @@ def test_fast_path_matches_oracle(name):
     f_err, c_err = util.max_err(out[0], want[0]), util.max_err(out[1], want[1])
     print(f"{name}: feats err {f_err:.3e} (scale {f_scale:.3e}), coors err {c_err:.3e} (update scale {c_scale:.3e})")
     assert np.isfinite(out[0].float().cpu().numpy()).all() and np.isfinite(out[1].float().cpu().numpy()).all()
-    assert f_err <= 3e-2 * f_scale
-    assert c_err <= 3e-2 * c_scale + 1e-3
+    assert f_err <= 1e-2 * f_scale
+    assert c_err <= 1e-2 * max(c_scale, 1.0)           # coordinates are O(1): where the update nearly cancels, 1e-2 absolute
 
 
 def test_fast_path_falls_back_to_fp32_simt_when_unsupported():
-    case = cases.build_case(cases.SPECS["knn_mean_fourier"])      # fourier features: not on the tensor-core path
+    case = cases.build_case(cases.SPECS["dense_mdim32"])          # m_dim = 32: not on the tensor-core path
     mod = util.make_module(case, torch.bfloat16)
-    out = util.run_module(mod, case, torch.bfloat16)
+    with pytest.warns(UserWarning, match="fp32"):
+        out = util.run_module(mod, case, torch.bfloat16)
     assert mod.last_path == "fp32-simt" and out[0].dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("name", ["d64_n160", "d64_edges4", "d128_mask"])
+def test_fast_path_row_range_equals_full_forward(name):
+    """Row-sharded use (EgnnLayerDesc.row_begin / row_end): rows inside the range are bit-identical to the full
+    forward's, rows outside keep the inputs."""
+    case, mod, full = run_fast(FAST_SPECS[name])
+    ins = case["inputs"]
+    n = ins["feats"].shape[1]
+    t = lambda key: util.to_torch(ins.get(key), torch.bfloat16, "cuda")
+    for (r0, r1) in [(0, n // 3), (n // 3, n - 5), (n - 5, n), (7, 8)]:
+        with torch.no_grad():
+            f, x = mod(t("feats"), t("coors"), t("edges"), mask=t("mask"), _rows=(r0, r1))
+        assert mod.last_path == "bf16-tcgen05"
+        assert torch.equal(f[:, r0:r1], full[0][:, r0:r1]) and torch.equal(x[:, r0:r1], full[1][:, r0:r1])
+        keep = torch.ones(n, dtype=torch.bool, device="cuda"); keep[r0:r1] = False
+        assert torch.equal(f[:, keep], t("feats")[:, keep]) and torch.equal(x[:, keep].float(), t("coors")[:, keep].float())
 
 
 def test_fast_equivariance():
