@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 DTYPE_F32, DTYPE_F64, DTYPE_BF16 = 0, 1, 2
 
@@ -100,6 +100,12 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "egnn_gemm_bf16": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                  C.c_void_p, C.c_int32, C.c_void_p]),
+    "egnn_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_size_t, _P(C.c_void_p), C.c_void_p]),
+    "egnn_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "egnn_comm_allgather": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_void_p),
+                                      C.c_void_p]),
+    "egnn_comm_status": (C.c_int, [C.c_void_p, _P(C.c_int32)]),
+    "egnn_comm_destroy": (C.c_int, [C.c_void_p]),
     "egnn_profile_enable": (C.c_int, [C.c_int]),
     "egnn_profile_read": (C.c_int, [_P(C.c_float), _P(C.c_int32), _P(C.c_int64), C.c_int]),
 }

@@ -44,6 +44,12 @@ FastDims fast_dims(const EgnnLayerDesc& d) {
   return f;
 }
 
+// neighbour-list kernel: lean (distance only), edges (<= 4 continuous channels in registers), generic (everything else)
+int knn_mode(const FastDims& f) {
+  if (f.s.C == 3 && f.s.F == 0 && f.L == 0) return f.s.edge_dim == 0 ? TK_LEAN : (f.s.edge_dim <= TK_QE ? TK_EDGES : TK_GEN);
+  return TK_GEN;
+}
+
 // the lean instantiation of the dense kernel covers 3-D coordinates with the distance as the only per-pair channel
 bool pair_is_lean(const FastDims& f) { return f.s.C == 3 && f.QT == 1; }
 
@@ -77,11 +83,11 @@ int fast_supported(const EgnnLayerDesc& d) {
     if (f.QT > TP_QMAX) return EGNN_ERR_UNSUPPORTED;
     const size_t smem = pair_is_lean(f) ? tc_pair_smem_bytes<false>(f.Hp, 1) : tc_pair_smem_bytes<true>(f.Hp, f.QT, 1 + 2 * f.s.F);
     if (smem > 227 * 1024) return EGNN_ERR_UNSUPPORTED;
-  } else {                                                         // neighbour lists: tc_knn_kernel
-    if (d.label_dim != 0 || d.fourier != 0 || d.C != 3) return EGNN_ERR_UNSUPPORTED;
-    if (d.k > 32 || d.edge_dim > TK_QE) return EGNN_ERR_UNSUPPORTED;
-    if (tc_knn_smem_bytes(f.Hp, d.edge_dim > 0) > 226 * 1024) return EGNN_ERR_UNSUPPORTED;
-    if (!(f.s.row0 == 0 && f.s.row1 == d.N)) return EGNN_ERR_UNSUPPORTED;
+  } else {                                                         // neighbour lists: tc_knn_kernel<lean | edges | generic>
+    if (d.k > 32) return EGNN_ERR_UNSUPPORTED;
+    const int mode = knn_mode(f);
+    if (mode == TK_GEN && f.QT > TP_QMAX) return EGNN_ERR_UNSUPPORTED;
+    if (tc_knn_smem_bytes(f.Hp, mode, f.QT) > 227 * 1024) return EGNN_ERR_UNSUPPORTED;
   }
   return EGNN_OK;
 }
@@ -386,13 +392,17 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     } else {
       StageTimer tm(st, STAGE_SELECT);
       const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;
-      EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, 3, s.k, io.coors, io.mask, io.adj,
+      EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
                                    (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
       count_launch();
     }
     StageTimer tm(st, STAGE_PAIR);
     TcKnnArgs a{};
     a.B = s.B; a.N = s.N; a.Hp = f.Hp; a.ldn = f.Kn; a.dim = s.dim; a.k = s.k; a.edge_dim = s.edge_dim;
+    a.C = s.C; a.Q = f.QT; a.F = s.F; a.num_labels = f.L; a.row0 = r0; a.row1 = r1;
+    a.labels = f.L > 0 ? io.edge_labels : nullptr;
+    if (f.L > 0 && !io.edge_labels) return EGNN_ERR_NULL;
+    if (s.edge_dim > 0 && !io.edges) return EGNN_ERR_NULL;
     a.flags = d.flags; a.has_mask = io.mask != nullptr; a.clamp = (float)d.clamp;
     a.Atab = Atab; a.Btab = Btab;
     a.wdh = reinterpret_cast<const float*>(pk + L.wq);                       // row 0 of the Wq table (no fourier here)
@@ -405,15 +415,23 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     a.nbr_idx = nbr_idx; a.nbr_ok = nbr_ok;
     a.m_out = uf ? node_in + s.dim : nullptr;
     a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
-    const bool ed = s.edge_dim > 0;
-    const size_t smem = tc_knn_smem_bytes(f.Hp, ed);
-    if (ed) EGNN_TRY((ensure_dyn_smem<3>(tc_knn_kernel<true>, smem)));
-    else EGNN_TRY((ensure_dyn_smem<4>(tc_knn_kernel<false>, smem)));
-    dim3 grid(ceil_div(s.N, TK_ROWS), s.B);
-    if (ed) tc_knn_kernel<true><<<grid, TK_THREADS, smem, st>>>(a);
-    else tc_knn_kernel<false><<<grid, TK_THREADS, smem, st>>>(a);
-    EGNN_LAUNCH_CHECK();
-    count_launch();
+    const int mode = knn_mode(f);
+    const size_t smem = tc_knn_smem_bytes(f.Hp, mode, f.QT);
+    dim3 grid(ceil_div(R, TK_ROWS), s.B);
+    if (R > 0) {
+      if (mode == TK_LEAN) {
+        EGNN_TRY((ensure_dyn_smem<3>(tc_knn_kernel<TK_LEAN>, smem)));
+        tc_knn_kernel<TK_LEAN><<<grid, TK_THREADS, smem, st>>>(a);
+      } else if (mode == TK_EDGES) {
+        EGNN_TRY((ensure_dyn_smem<4>(tc_knn_kernel<TK_EDGES>, smem)));
+        tc_knn_kernel<TK_EDGES><<<grid, TK_THREADS, smem, st>>>(a);
+      } else {
+        EGNN_TRY((ensure_dyn_smem<5>(tc_knn_kernel<TK_GEN>, smem)));
+        tc_knn_kernel<TK_GEN><<<grid, TK_THREADS, smem, st>>>(a);
+      }
+      EGNN_LAUNCH_CHECK();
+      count_launch();
+    }
   }
   StageTimer post(st, STAGE_NODE_POST);
   __nv_bfloat16* fout = static_cast<__nv_bfloat16*>(io.feats_out);

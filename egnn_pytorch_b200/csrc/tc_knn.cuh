@@ -12,7 +12,11 @@
 //     MMA rows are 4 query rows x 32 slots and the reduction over j is a single warp shuffle tree;
 //   * the B' row of every pair is gathered from L2 (8-byte pieces, contiguous across the 4 lanes that share a
 //     pair) and used once: each 64-channel round re-fills its B' registers for the next chunk right after use;
-//   * up to 4 continuous edge channels per pair are folded in on the CUDA cores (We from shared memory).
+//   * up to 4 continuous edge channels per pair are folded in on the CUDA cores (We from shared memory);
+//   * MODE 2 is the generic instantiation: any number (<= TP_QMAX) of per-pair scalar channels -- squared distance,
+//     fourier features (egnn_pytorch.py:34-41), continuous edge channels, one-hot adjacency-degree labels (the folded
+//     `adj_emb` of EGNN_Network, :430-432) -- kept per slot in a small per-warp shared-memory tile, and any coordinate
+//     dimension C <= 8.  BASELINE config 5 (only_sparse_neighbors + num_adj_degrees) runs here.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -29,13 +33,18 @@ constexpr int TK_THREADS = 512;
 constexpr int TK_WGCOLS = 128;     // 16 accumulator + 3 x 32 operand columns (+16 spare)
 constexpr int TK_QE = 4;           // edge channels folded per pair (edge_dim <= 4, zero padded)
 
+constexpr int TK_LEAN = 0, TK_EDGES = 1, TK_GEN = 2;
+
 struct TcKnnArgs {
   int B, N, Hp, ldn, dim, k, edge_dim;
+  int C, Q, F, num_labels;         // generic instantiation: Q = 1 + 2F + edge_dim + num_labels channels, C coordinates
+  int row0, row1;                  // i-rows [row0, row1) of every graph are evaluated
   uint32_t flags; int has_mask; float clamp;
   const float* Atab;               // [M][Hp]  0.5 (h W1_i^T + b1)
   const __nv_bfloat16* Btab;       // [M][Hp]  0.5 h W1_j^T
-  const float* wdh;                // [Hp]     0.5 W1[:, 2dim]
-  const float* weh;                // [TK_QE][Hp]  0.5 W1[:, 2dim+1+q]  (zero rows beyond edge_dim)
+  const float* wdh;                // [Hp]     0.5 W1[:, 2dim]                        (= row 0 of the packed Wq table)
+  const float* weh;                // [TK_QE][Hp]  0.5 W1[:, 2dim+1+q]  (zero rows beyond edge_dim; rows 1..4 of Wq)
+  const uint8_t* labels;           // [B][N][N] | null  (generic instantiation)
   const __nv_bfloat16* w2p;        // W2 in core-matrix order
   const float* epi;
   const float* coors;              // [B][N][3]
@@ -47,27 +56,35 @@ struct TcKnnArgs {
   float* coors_out;                // [B][N][3] | null
 };
 
-inline size_t tc_knn_smem_bytes(int Hp, bool has_edges) {
+// channels of the Wq table staged in shared memory: 1 (lean), 1 + TK_QE (edges), Q (generic)
+inline int tc_knn_wq_rows(int mode, int Q) { return mode == TK_LEAN ? 1 : mode == TK_EDGES ? 1 + TK_QE : Q; }
+
+inline size_t tc_knn_smem_bytes(int Hp, int mode, int Q = 1) {
   size_t n = 0;
   n += (size_t)Hp * 32;                       // W2 slabs
   n += (size_t)TK_ROWS * Hp * 4;              // A rows (fp32)
-  n += (size_t)Hp * 4;                        // wd
-  n += has_edges ? (size_t)TK_QE * Hp * 4 : 0;   // We
+  n += (size_t)tc_knn_wq_rows(mode, Q) * Hp * 4;   // wd | We | generic Wq
   n += (size_t)TP_EPI_FLOATS * 4;             // epilogue constants
+  n += mode == TK_GEN ? (size_t)TK_ROWS * Q * 32 * 4 : 0;   // per-warp scalar tile [Q][32 slots]
   n += 64 + 32 * 8;                           // tmem pointer, mbarriers
   return n + 128;
 }
 
-template <bool EDGES>
+template <int MODE>
 __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a) {
+  constexpr bool EDGES = MODE == TK_EDGES, GEN = MODE == TK_GEN;
+  constexpr int NX = GEN ? TP_CMAX : 3;                                       // coordinate registers
+  constexpr int PW = GEN ? 16 + TP_CMAX + 1 : 20;                             // reduced record: 16 m | coords | count
   extern __shared__ __align__(128) unsigned char sm[];
   const int Hp = a.Hp, N = a.N, K = a.k;
+  const int C = GEN ? a.C : 3, Q = GEN ? a.Q : 1;
   unsigned char* w2s = sm;
   float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [16][Hp]
-  float* wds = As + (size_t)TK_ROWS * Hp;                                     // [Hp]
+  float* wds = As + (size_t)TK_ROWS * Hp;                                     // [Hp]  (generic: Wq [Q][Hp])
   float* wes = wds + Hp;                                                      // [QE][Hp] (EDGES only)
-  float* epi = wes + (EDGES ? TK_QE * Hp : 0);
-  uint32_t* misc = reinterpret_cast<uint32_t*>(epi + TP_EPI_FLOATS);          // [0] tmem pointer
+  float* epi = wds + (size_t)(GEN ? Q : EDGES ? 1 + TK_QE : 1) * Hp;
+  float* stile = epi + TP_EPI_FLOATS;                                         // [16 warps][Q][32] (GEN only)
+  uint32_t* misc = reinterpret_cast<uint32_t*>(stile + (GEN ? TK_ROWS * Q * 32 : 0));   // [0] tmem pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 16);
   uint64_t* full = bars;                      // [4][SLOTS]
   uint64_t* empty = bars + 4 * TK_SLOTS;      // [4][SLOTS]
@@ -75,8 +92,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   uint64_t* ldbar = accdone + 4;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, i0 = blockIdx.x * TK_ROWS;
-  const int rows_valid = min(TK_ROWS, N - i0);
+  const int b = blockIdx.y, i0 = a.row0 + blockIdx.x * TK_ROWS;
+  const int rows_valid = min(TK_ROWS, a.row1 - i0);
   const int nchunks = (Hp + TK_KC - 1) / TK_KC;
   const int nsl_last = (Hp - (nchunks - 1) * TK_KC) / 16;        // valid K slabs of the last chunk (Hp is a multiple of 16)
   const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
@@ -96,7 +113,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   const uint32_t tmem = misc[0];
 
   if (tid == 0) {
-    const uint32_t w2_bytes = (uint32_t)Hp * 32, as_bytes = (uint32_t)rows_valid * Hp * 4, wd_bytes = (uint32_t)Hp * 4;
+    const uint32_t w2_bytes = (uint32_t)Hp * 32, as_bytes = (uint32_t)rows_valid * Hp * 4;
+    const uint32_t wd_bytes = (uint32_t)(GEN ? Q : 1) * Hp * 4;              // generic: the whole Wq table (rows are contiguous)
     const uint32_t we_bytes = EDGES ? (uint32_t)TK_QE * Hp * 4 : 0u;
     tc::mbar_arrive_expect_tx(ldbar, w2_bytes + as_bytes + wd_bytes + we_bytes);
     auto bulk = [&](uint32_t dst, const unsigned char* src, uint32_t bytes) {
@@ -118,7 +136,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   const bool iv = warp < rows_valid;
   const int i = i0 + (iv ? warp : 0);
   const size_t nodei = (size_t)b * N + i;
-  const float xi0 = a.coors[nodei * 3 + 0], xi1 = a.coors[nodei * 3 + 1], xi2 = a.coors[nodei * 3 + 2];
+  float xi[NX];
+#pragma unroll
+  for (int c = 0; c < NX; ++c) xi[c] = (!GEN || c < C) ? a.coors[nodei * C + c] : 0.f;
   const bool mask_i = iv && (a.has_mask ? a.mask[nodei] != 0 : true);
 
   // ---- pair mapping: lane = neighbour slot
@@ -131,8 +151,32 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     if (j < 0) { j = i; sv = false; }                 // empty slot of a caller-supplied neighbour list
   }
   const size_t nodej = (size_t)b * N + j;
-  const float r0 = xi0 - a.coors[nodej * 3 + 0], r1 = xi1 - a.coors[nodej * 3 + 1], r2 = xi2 - a.coors[nodej * 3 + 2];
-  const float dmine = r0 * r0 + r1 * r1 + r2 * r2;
+  float rel[NX];
+  float dmine = 0.f;
+#pragma unroll
+  for (int c = 0; c < NX; ++c) {
+    rel[c] = (!GEN || c < C) ? xi[c] - a.coors[nodej * C + c] : 0.f;
+    dmine = fmaf(rel[c], rel[c], dmine);
+  }
+  float* myS = stile + (size_t)warp * Q * 32;          // generic: this warp's per-slot scalar channels
+  if (GEN) {
+    myS[lane] = dmine;
+    int q = 1;
+    for (int f = 0; f < a.F; ++f) {                                                               // :34-41
+      const float sc = dmine * exp2f(-(float)f);
+      myS[(q + f) * 32 + lane] = sinf(sc);
+      myS[(q + a.F + f) * 32 + lane] = cosf(sc);
+    }
+    q += 2 * a.F;
+    const size_t pij = ((size_t)b * N + i) * N + j;
+    for (int e = 0; e < a.edge_dim; ++e) myS[(q + e) * 32 + lane] = __bfloat162float(a.edges[pij * a.edge_dim + e]);
+    q += a.edge_dim;
+    if (a.num_labels > 0) {
+      const int lab = a.labels[pij];
+      for (int l = 0; l < a.num_labels; ++l) myS[(q + l) * 32 + lane] = (l == lab) ? 1.f : 0.f;
+    }
+    __syncwarp();
+  }
   // ---- fragment mapping: rows (slots) lr + 8*rho of this warp; fetch their j, d, edges by shuffle / gather
   int jf[4];
   float dr[4];
@@ -204,7 +248,23 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
         const bool slv = sl < nsl;                          // slabs beyond Hp (last chunk only): zeros, never multiplied
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 av = slv ? *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16) : zero4;
-        const float4 wv = slv ? *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4) : zero4;
+        const float4 wv = (slv && !GEN) ? *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4) : zero4;
+        float zg[2][4];                                      // generic: A' + sum_q Wq[q] s_q for the two slots of this half
+        if (GEN) {
+#pragma unroll
+          for (int r2 = 0; r2 < 2; ++r2) { zg[r2][0] = av.x; zg[r2][1] = av.y; zg[r2][2] = av.z; zg[r2][3] = av.w; }
+          if (slv) {
+#pragma unroll 1
+            for (int q = 0; q < Q; ++q) {
+              const float4 wq4 = *reinterpret_cast<const float4*>(wds + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
+              const float s0 = myS[q * 32 + lr + 16 * half], s1 = myS[q * 32 + lr + 16 * half + 8];
+              zg[0][0] = fmaf(wq4.x, s0, zg[0][0]); zg[0][1] = fmaf(wq4.y, s0, zg[0][1]);
+              zg[0][2] = fmaf(wq4.z, s0, zg[0][2]); zg[0][3] = fmaf(wq4.w, s0, zg[0][3]);
+              zg[1][0] = fmaf(wq4.x, s1, zg[1][0]); zg[1][1] = fmaf(wq4.y, s1, zg[1][1]);
+              zg[1][2] = fmaf(wq4.z, s1, zg[1][2]); zg[1][3] = fmaf(wq4.w, s1, zg[1][3]);
+            }
+          }
+        }
         float4 we[TK_QE];
         if (EDGES) {
 #pragma unroll
@@ -216,6 +276,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
           const uint2 bb = Bc[rho][sl];
           const float d = dr[rho];
           float z0 = fmaf(wv.x, d, av.x), z1 = fmaf(wv.y, d, av.y), z2 = fmaf(wv.z, d, av.z), z3 = fmaf(wv.w, d, av.w);
+          if (GEN) { z0 = zg[r2][0]; z1 = zg[r2][1]; z2 = zg[r2][2]; z3 = zg[r2][3]; }
           if (EDGES) {
 #pragma unroll
             for (int q = 0; q < TK_QE; ++q) {
@@ -286,28 +347,29 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
       if (!sv) w = 0.f;                                                  // padding slots carry nothing, clamp or not
       if (a.flags & EGNN_FLAG_NORM_COORS) w *= sc[2] / fmaxf(sqrtf(dmine), 1e-8f);
     }
-    float v[20];
-    v[16] = w * r0; v[17] = w * r1; v[18] = w * r2;
-    v[19] = pm ? 1.f : 0.f;
+    float v[PW];
+#pragma unroll
+    for (int c = 0; c < NX; ++c) v[16 + c] = w * rel[c];
+    v[PW - 1] = pm ? 1.f : 0.f;
 #pragma unroll
     for (int o = 0; o < 16; ++o) v[o] = pm ? m[o] : 0.f;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1)
 #pragma unroll
-      for (int o = 0; o < 20; ++o) v[o] += __shfl_xor_sync(0xffffffffu, v[o], off);
+      for (int o = 0; o < PW; ++o) v[o] += __shfl_xor_sync(0xffffffffu, v[o], off);
     if (iv) {
       if (upd_feats && lane < 16) {
         float inv = 1.f;
-        if (a.flags & EGNN_FLAG_POOL_MEAN) inv = a.has_mask ? (v[19] > 0.f ? 1.f / v[19] : 0.f) : 1.f / (float)K;
+        if (a.flags & EGNN_FLAG_POOL_MEAN) inv = a.has_mask ? (v[PW - 1] > 0.f ? 1.f / v[PW - 1] : 0.f) : 1.f / (float)K;
         float mine = 0.f;
 #pragma unroll
         for (int o = 0; o < 16; ++o) if (o == lane) mine = v[o];
         a.m_out[nodei * a.ldn + lane] = __float2bfloat16(mine * inv);
       }
       if (upd_coors && lane == 0) {
-        a.coors_out[nodei * 3 + 0] = xi0 + v[16];
-        a.coors_out[nodei * 3 + 1] = xi1 + v[17];
-        a.coors_out[nodei * 3 + 2] = xi2 + v[18];
+#pragma unroll
+        for (int c = 0; c < NX; ++c)
+          if (!GEN || c < C) a.coors_out[nodei * C + c] = xi[c] + v[16 + c];
       }
     }
   }

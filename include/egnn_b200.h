@@ -15,7 +15,8 @@
  *    outlives the call and never synchronises the stream (HOST-buffer entry excepted);
  *  - every entry returns 0 on success or a negative EGNN_ERR_* code and never throws;
  *  - all tensors are contiguous, row-major, in the layouts written next to each field;
- *  - re-entrant across streams and devices; no mutable global state.
+ *  - re-entrant across streams and devices; the only mutable global state is a mutex-guarded, write-once per-device
+ *    cache of kernel attributes / SM counts and the opt-in profiler below.
  */
 #ifndef EGNN_B200_H_
 #define EGNN_B200_H_
@@ -27,7 +28,8 @@
 extern "C" {
 #endif
 
-#define EGNN_ABI_VERSION 2   /* 2: EgnnLayerIO grew nbr_idx + pre2_out; backward entry points added */
+#define EGNN_ABI_VERSION 3   /* 2: EgnnLayerIO grew nbr_idx + pre2_out; backward entry points added
+                                3: peer-memory all-gather communicator (egnn_comm_*) */
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define EGNN_OK                 0
@@ -213,6 +215,30 @@ int egnn_adj_expand(int32_t B, int32_t N, int32_t num_degrees, const uint8_t* ad
  * act 0 = none / 1 = SiLU, out fp32 (out_f32 = 1) or bf16. */
 int egnn_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, const void* W, const float* bias,
                    float scale, int32_t act, void* out, int32_t out_f32, void* stream);
+
+/*
+ * Peer-memory all-gather over NVLink for the ROW-SHARDED single graph (reference
+ * semantics: the all-pairs pass of egnn_pytorch.py:232-233 runs over ALL nodes, so every rank needs every rank's
+ * coordinates and features on the j side).  One process per GPU.  The communicator is the one object of this library
+ * that owns device memory beyond a call: a gather buffer (2 x payload_bytes, double-buffered by call parity) that the
+ * peers map with CUDA IPC.
+ *   egnn_comm_create   -> allocates the buffer on the current device, returns the communicator and a 64-byte IPC handle;
+ *                         exchange the handles of all ranks out of band (torch.distributed.all_gather_object) ...
+ *   egnn_comm_connect  -> ... and pass all of them (world x 64 bytes, rank order) to map the peers' buffers.
+ *   egnn_comm_allgather-> ONE kernel on `stream`: copies this rank's `nseg` segments src[s] (bytes[s], multiples of 4)
+ *                         to byte offset dst_off[s] of EVERY rank's buffer with P2P stores over NVLink, raises this rank's
+ *                         epoch flag in every peer and waits (on the device) for every peer's flag.  Kernels enqueued
+ *                         after it on the same stream see the complete buffer at *gathered_out (valid until the call
+ *                         after next).  Every rank must make the same sequence of calls.  No host synchronisation.
+ *   egnn_comm_status   -> 0, or 1 if a wait timed out (a peer never arrived); synchronises.
+ */
+#define EGNN_IPC_HANDLE_BYTES 64
+int egnn_comm_create(int32_t world, int32_t rank, size_t payload_bytes, void** comm_out, void* ipc_handle_out);
+int egnn_comm_connect(void* comm, const void* all_handles);
+int egnn_comm_allgather(void* comm, int32_t nseg, const void* const* src, const size_t* dst_off, const size_t* bytes,
+                        void** gathered_out, void* stream);
+int egnn_comm_status(void* comm, int32_t* status_out);
+int egnn_comm_destroy(void* comm);
 
 /* Diagnostics for benchmarks: when enabled, every egnn_layer_forward brackets its stages
  * (0 neighbour select, 1 per-node tables, 2 fused edge kernel, 3 node update) with CUDA events

@@ -63,6 +63,22 @@ FAST_SPECS = {
                             mask="full"),
     "knn_mean_nomask": dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=7, m_pool_method="mean"), B=1, N=33, seed=87,
                             init="xavier"),
+    # --- the generic instantiation of the neighbour-list kernel (fourier, > 4 edge channels, C != 3, degree labels)
+    "knn_fourier2":    dict(kind=L, cfg=dict(dim=64, num_nearest_neighbors=7, fourier_features=2), B=2, N=60, seed=60, init="xavier",
+                            mask="padded"),
+    "knn_c5_e2":       dict(kind=L, cfg=dict(dim=32, num_nearest_neighbors=6, edge_dim=2, norm_coors=True), B=2, N=40, C=5, seed=61,
+                            init="xavier"),
+    "knn_e6_soft":     dict(kind=L, cfg=dict(dim=32, num_nearest_neighbors=5, edge_dim=6, soft_edges=True, m_pool_method="mean"), B=1, N=50,
+                            seed=62, init="xavier", mask="random"),
+    "net_c5_like":     dict(kind="network", cfg=dict(depth=3, dim=32, num_tokens=21, num_adj_degrees=3, adj_dim=8,
+                                                     only_sparse_neighbors=True), B=1, N=96, seed=63, adj="chain", mask="full"),
+    "net_c5_xavier":   dict(kind="network", cfg=dict(depth=2, dim=32, num_tokens=21, num_adj_degrees=2, adj_dim=4, edge_dim=2,
+                                                     num_edge_tokens=4, only_sparse_neighbors=True), B=2, N=40, seed=64, init="xavier",
+                            adj="chain", edges=True, mask="padded"),
+    # depth 1: with more layers the bf16 coordinate round-off of layer 1 may flip a near-tie of layer 2's top-k, which is a
+    # property of re-selecting neighbours, not of the kernels (the full c3 shape is covered in test_gpu_baseline_configs)
+    "net_c3_like":     dict(kind="network", cfg=dict(depth=1, dim=32, num_tokens=21, num_positions=128, num_nearest_neighbors=8,
+                                                     coor_weights_clamp_value=2.0), B=1, N=128, seed=65, mask="full"),
 }
 
 
@@ -108,7 +124,7 @@ def test_fast_path_falls_back_to_fp32_simt_when_unsupported():
     assert mod.last_path == "fp32-simt" and out[0].dtype == torch.bfloat16
 
 
-@pytest.mark.parametrize("name", ["d64_n160", "d64_edges4", "d128_mask"])
+@pytest.mark.parametrize("name", ["d64_n160", "d64_edges4", "d128_mask", "knn_d64_k8", "knn_d64_k32_e4", "knn_fourier2"])
 def test_fast_path_row_range_equals_full_forward(name):
     """Row-sharded use (EgnnLayerDesc.row_begin / row_end): rows inside the range are bit-identical to the full
     forward's, rows outside keep the inputs."""

@@ -18,6 +18,7 @@ def _worker(rank, world, port, q):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         torch.cuda.set_device(rank)
+        torch.set_grad_enabled(False)                # inference: row ranges are a forward-only feature
         dev = torch.device("cuda", rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         from egnn_pytorch_b200 import parallel
@@ -43,6 +44,33 @@ def _worker(rank, world, port, q):
             want = cases.run_oracle(case)
             util.assert_close(f_loc, want[0][:, r0:r1], atol=2e-5, rtol=1e-4, what=f"row-sharded {name} feats")
             util.assert_close(x_loc, want[1][:, r0:r1], atol=2e-5, rtol=1e-4, what=f"row-sharded {name} coors")
+        # ---- the same row sharding with the library's peer-memory all-gather over NVLink (egnn_comm_*): two layer calls
+        #      back to back (exercises the double-buffered epochs), fp32 SIMT and bf16 tensor-core kernels, dense and kNN
+        for name, dtype in (("dense_mask_padded", torch.float32), ("knn_norm_coors", torch.float32),
+                            ("dense_xavier", torch.bfloat16), ("knn_basic", torch.bfloat16)):
+            case = cases.build_case(cases.SPECS[name])
+            if dtype == torch.bfloat16 and case["cfg"]["dim"] % 8:
+                continue
+            mod = util.make_module(case, dtype, device=dev)
+            ins = {k: util.to_torch(v, dtype, dev) for k, v in case["inputs"].items()}
+            ins["coors"] = ins["coors"].float()
+            b, n, d = ins["feats"].shape
+            r0, r1 = parallel.shard_range(n, rank, world)
+            _, payload = parallel.row_payload_layout(n, ins["coors"].shape[-1], d, ins["feats"].element_size(), b)
+            comm = parallel.PeerComm(payload)
+            kw = dict(mask=ins.get("mask"))
+            if ins.get("edges") is not None:
+                kw["edges"] = ins["edges"]
+            with torch.no_grad():
+                full_f, full_x = mod(ins["feats"], ins["coors"], ins.get("edges"), mask=ins.get("mask"))
+                f1, x1 = parallel.row_sharded_layer_peer(comm, mod, ins["feats"][:, r0:r1], ins["coors"][:, r0:r1], n, **kw)
+                f2, x2 = parallel.row_sharded_layer_peer(comm, mod, f1, x1, n, **kw)          # second layer call on the outputs
+                g_f, g_x = mod(full_f, full_x.float(), ins.get("edges"), mask=ins.get("mask"))
+            torch.cuda.synchronize(dev)
+            assert comm.status() == 0
+            assert torch.equal(f1, full_f[:, r0:r1]) and torch.equal(x1.float(), full_x[:, r0:r1].float()), name
+            assert torch.equal(f2, g_f[:, r0:r1]) and torch.equal(x2.float(), g_x[:, r0:r1].float()), name
+            comm.close()
         dist.barrier()
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
