@@ -79,6 +79,30 @@ class LayerGrads(C.Structure):
                 ("g_coors", C.c_void_p), ("g_edges", C.c_void_p), ("w", LayerWeightGrads)]
 
 
+GA_WEIGHT_FIELDS = ("norm_seq_g", "norm_seq_b", "norm_q_g", "norm_q_b", "a1_wq", "a1_wkv", "a1_wo", "a1_bo", "a2_wq", "a2_wkv", "a2_wo",
+                    "a2_bo", "ff_ln_g", "ff_ln_b", "ff_w1", "ff_b1", "ff_w2", "ff_b2")
+# GlobalLinearAttention state-dict key (reference naming) -> EgnnGlobalAttnWeights field
+GA_STATE_KEY_TO_FIELD = {
+    "norm_seq.weight": "norm_seq_g", "norm_seq.bias": "norm_seq_b", "norm_queries.weight": "norm_q_g", "norm_queries.bias": "norm_q_b",
+    "attn1.to_q.weight": "a1_wq", "attn1.to_kv.weight": "a1_wkv", "attn1.to_out.weight": "a1_wo", "attn1.to_out.bias": "a1_bo",
+    "attn2.to_q.weight": "a2_wq", "attn2.to_kv.weight": "a2_wkv", "attn2.to_out.weight": "a2_wo", "attn2.to_out.bias": "a2_bo",
+    "ff.0.weight": "ff_ln_g", "ff.0.bias": "ff_ln_b", "ff.1.weight": "ff_w1", "ff.1.bias": "ff_b1", "ff.3.weight": "ff_w2", "ff.3.bias": "ff_b2",
+}
+
+
+class GlobalAttnDesc(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("dtype", C.c_int32), ("B", C.c_int32), ("N", C.c_int32), ("T", C.c_int32),
+                ("dim", C.c_int32), ("heads", C.c_int32), ("dim_head", C.c_int32)]
+
+
+class GlobalAttnWeights(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in GA_WEIGHT_FIELDS]
+
+
+class GlobalAttnIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("queries", C.c_void_p), ("mask", C.c_void_p), ("x_out", C.c_void_p), ("queries_out", C.c_void_p)]
+
+
 # every symbol include/egnn_b200.h declares: (restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
@@ -100,6 +124,9 @@ SYMBOLS = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "egnn_gemm_bf16": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32,
                                  C.c_void_p, C.c_int32, C.c_void_p]),
+    "egnn_global_attn_workspace_bytes": (C.c_int, [C.POINTER(GlobalAttnDesc), C.POINTER(C.c_size_t)]),
+    "egnn_global_attn_forward": (C.c_int, [C.POINTER(GlobalAttnDesc), C.POINTER(GlobalAttnWeights), C.POINTER(GlobalAttnIO), C.c_void_p,
+                                           C.c_size_t, C.c_void_p]),
     "egnn_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_size_t, _P(C.c_void_p), C.c_void_p]),
     "egnn_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "egnn_comm_allgather": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_void_p), _P(C.c_size_t), _P(C.c_size_t), _P(C.c_void_p),

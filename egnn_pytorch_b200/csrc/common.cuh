@@ -68,6 +68,10 @@ template <> __device__ __forceinline__ float silu_acc<float>(float x) {
 template <> __device__ __forceinline__ double silu_acc<double>(double x) {
   return x / (1.0 + exp(-x));
 }
+// nn.GELU() (exact): 0.5 x (1 + erf(x / sqrt 2))   (GlobalLinearAttention's feed-forward, egnn_pytorch.py:127)
+template <typename T> __device__ __forceinline__ T gelu_acc(T x);
+template <> __device__ __forceinline__ float gelu_acc<float>(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+template <> __device__ __forceinline__ double gelu_acc<double>(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }
 template <typename T> __device__ __forceinline__ T sigmoid_acc(T x);
 template <> __device__ __forceinline__ float sigmoid_acc<float>(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 template <> __device__ __forceinline__ double sigmoid_acc<double>(double x) { return 1.0 / (1.0 + exp(-x)); }

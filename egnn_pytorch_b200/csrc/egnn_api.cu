@@ -12,6 +12,8 @@ namespace egnn {
 int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
                         const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
                         uint8_t* out_ok, cudaStream_t st);
+int adj_neighbors_dispatch(int B, int N, int k, const uint8_t* adj, int adj_batched, int32_t* out_idx, uint8_t* out_ok,
+                           cudaStream_t st);
 
 template <typename T, int MP, bool KNN>
 static int launch_pair(const PairArgs<T>& a, cudaStream_t st) {
@@ -75,8 +77,11 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
     StageTimer tm(st, STAGE_SELECT);
     count_launch();
     const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;     // :250
-    EGNN_TRY(knn_select_dispatch(d.dtype, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
-                                 (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
+    if ((d.flags & EGNN_FLAG_ONLY_SPARSE) && io.mask && io.adj)      // every slot top-k could add is masked out: row scan
+      EGNN_TRY(adj_neighbors_dispatch(s.B, s.N, s.k, io.adj, (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, nbr_idx, nbr_ok, st));
+    else
+      EGNN_TRY(knn_select_dispatch(d.dtype, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
+                                   (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
   }
   // 2. per-node tables  A = h W1[:, :dim]^T + b1,  B = h W1[:, dim:2dim]^T   (split of :287's Linear-1)
   {

@@ -16,6 +16,8 @@ namespace egnn {
 int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* coors, const uint8_t* mask,
                         const uint8_t* adj, int adj_batched, double valid_radius, int32_t* out_idx,
                         uint8_t* out_ok, cudaStream_t st);
+int adj_neighbors_dispatch(int B, int N, int k, const uint8_t* adj, int adj_batched, int32_t* out_idx, uint8_t* out_ok,
+                           cudaStream_t st);
 
 namespace {
 
@@ -392,8 +394,11 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     } else {
       StageTimer tm(st, STAGE_SELECT);
       const double vr = (d.flags & EGNN_FLAG_ONLY_SPARSE) ? 0.0 : d.valid_radius;
-      EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
-                                   (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
+      if ((d.flags & EGNN_FLAG_ONLY_SPARSE) && io.mask && io.adj)      // every slot top-k could add is masked out: row scan
+        EGNN_TRY(adj_neighbors_dispatch(s.B, s.N, s.k, io.adj, (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, nbr_idx, nbr_ok, st));
+      else
+        EGNN_TRY(knn_select_dispatch(EGNN_DTYPE_F32, s.B, s.N, s.C, s.k, io.coors, io.mask, io.adj,
+                                     (d.flags & EGNN_FLAG_ADJ_BATCHED) ? 1 : 0, vr, nbr_idx, nbr_ok, st));
       count_launch();
     }
     StageTimer tm(st, STAGE_PAIR);

@@ -264,6 +264,67 @@ int knn_select_dispatch(int32_t dtype, int B, int N, int C, int k, const void* c
   return launch_select<float>(B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx, out_ok, st);
 }
 
+// only_sparse_neighbors WITH a node mask (egnn_pytorch.py:249-260, :296): valid_radius is 0, so the only slots whose
+// pair mask can be true are the node itself (rank -1) and its adjacent nodes (rank 0, ties to the lowest index) --
+// whatever top-k fills the remaining slots with is masked out (nbhd_mask = rank <= 0).  Those lists need no distance
+// ranking at all: one warp scans the node's adjacency row in index order.  Slot 0 = self, then the adjacent nodes
+// ascending (exactly the top-k order of the valid slots, truncated at k like top-k); unused slots point at the node
+// itself with ok = 0.  Replaces an O(N^2) ranking pass (295 us per layer at N = 8192, BASELINE config 5) by a row scan.
+__global__ void __launch_bounds__(256) adj_neighbors_kernel(int B, int N, int k, const uint8_t* __restrict__ adj, int adj_batched,
+                                                            int32_t* __restrict__ out_idx, uint8_t* __restrict__ out_ok) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (row >= B * N) return;
+  const int b = row / N, i = row % N;
+  const uint8_t* a = adj + ((size_t)(adj_batched ? b : 0) * N + i) * N;
+  int32_t* oi = out_idx + (size_t)row * k;
+  uint8_t* ok = out_ok ? out_ok + (size_t)row * k : nullptr;
+  if (lane == 0) { oi[0] = i; if (ok) ok[0] = 1; }
+  int pos = 1;
+  const bool wide = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(adj) & 3) == 0);
+  if (wide) {
+    const uint32_t* a4 = reinterpret_cast<const uint32_t*>(a);
+    for (int j0 = 0; j0 < N && pos < k; j0 += 128) {
+      const int j = j0 + lane * 4;
+      uint32_t w = j < N ? __ldg(a4 + j / 4) : 0u;
+      // clear the node's own entry; count and place this lane's up to four hits
+      uint32_t bits = 0;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) if (((w >> (8 * t)) & 0xffu) && j + t != i) bits |= 1u << t;
+      const int cnt = __popc(bits);
+      int pre = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+      const int total = __shfl_sync(0xffffffffu, pre, 31);
+      int p = pos + pre - cnt;
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (bits & (1u << t)) { if (p < k) { oi[p] = j + t; if (ok) ok[p] = 1; } ++p; }
+      pos += total;
+    }
+  } else {
+    for (int j0 = 0; j0 < N && pos < k; j0 += 32) {
+      const int j = j0 + lane;
+      const bool hit = j < N && a[j] != 0 && j != i;
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      const int p = pos + __popc(m & ((1u << lane) - 1u));
+      if (hit && p < k) { oi[p] = j; if (ok) ok[p] = 1; }
+      pos += __popc(m);
+    }
+  }
+  pos = pos < k ? pos : k;
+  for (int p = pos + lane; p < k; p += 32) { oi[p] = i; if (ok) ok[p] = 0; }
+}
+
+int adj_neighbors_dispatch(int B, int N, int k, const uint8_t* adj, int adj_batched, int32_t* out_idx, uint8_t* out_ok,
+                           cudaStream_t st) {
+  if (!adj || !out_idx) return EGNN_ERR_NULL;
+  if (B <= 0 || N <= 0 || k <= 0 || k > N) return EGNN_ERR_SHAPE;
+  const long long threads = (long long)B * N * 32;
+  adj_neighbors_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(B, N, k, adj, adj_batched, out_idx, out_ok);
+  EGNN_LAUNCH_CHECK();
+  return EGNN_OK;
+}
+
 }  // namespace egnn
 
 extern "C" int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, int32_t k, const void* coors,

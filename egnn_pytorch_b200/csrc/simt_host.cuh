@@ -74,9 +74,22 @@ static int ensure_dynamic_smem(K kernel, size_t smem) {
 template <typename T, int ACT, bool RES>
 static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, const T* R, int ldr, T* C,
                        int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st) {
-  if (Mr <= 16) {
-    gemm_skinny_kernel<T, ACT, RES><<<ceil_div(ceil_div(Nout, SKINNY_COLS) * 32, 256), 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv,
-                                                                            Nout, K, map);
+  constexpr int V = 16 / (int)sizeof(T);
+  const size_t skinny_smem = (size_t)16 * ((K + V - 1) / V * V) * sizeof(T);
+  if (Mr <= 16 && skinny_smem <= 96 * 1024) {
+    // columns per warp: as many as still give about one CTA per SM (the kernel is bound by weight streaming)
+    const int cols = Nout >= 148 * SKINNY_WARPS * 4 ? 4 : (Nout >= 148 * SKINNY_WARPS * 2 ? 2 : 1);
+    const int grid = ceil_div(Nout, SKINNY_WARPS * cols);
+    if (cols == 4) {
+      EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 4>, skinny_smem));
+      gemm_skinny_kernel<T, ACT, RES, 4><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+    } else if (cols == 2) {
+      EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 2>, skinny_smem));
+      gemm_skinny_kernel<T, ACT, RES, 2><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+    } else {
+      EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 1>, skinny_smem));
+      gemm_skinny_kernel<T, ACT, RES, 1><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+    }
     EGNN_LAUNCH_CHECK();
     count_launch();
     return EGNN_OK;

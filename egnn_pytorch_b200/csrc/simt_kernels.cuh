@@ -81,7 +81,7 @@ struct RowMap {
   __device__ __forceinline__ size_t operator()(int r) const { return (size_t)(r / Rr) * N + row0 + (r % Rr); }
 };
 
-template <typename T, int ACT /*0 none, 1 silu*/, bool RES>
+template <typename T, int ACT /*0 none, 1 silu, 2 gelu (exact, erf)*/, bool RES>
 __global__ void __launch_bounds__(256)
 gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
                const T* __restrict__ bias, const T* __restrict__ R, int ldr,
@@ -133,6 +133,7 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
       if (col < Nv) {
         v = acc[i][j] + (bias ? bias[col] : T(0));
         if (ACT == 1) v = silu_acc<T>(v);
+        if (ACT == 2) v = gelu_acc<T>(v);
         if (RES) v += R[row * ldr + col];
       }
       Cout[row * ldo + col] = v;
@@ -144,62 +145,93 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
 // Same contract as gemm_nt_kernel for few rows (Mr <= 16, the latency-bound configs c1/README example):
 // one warp per output column n reads W[n, :] once, coalesced, and keeps all Mr row sums in registers.
 // =====================================================================================
-constexpr int SKINNY_COLS = 4;      // output columns per warp: every A value loaded feeds 4 FMAs
+// The latency-bound configs (BASELINE c1: 16 nodes, 12.7 MB of fp32 weights) are bound by how fast the WEIGHTS stream
+// from L2 / HBM: one CTA = 4 warps x COLS output columns, the <= 16 activation rows staged once in shared memory, every
+// lane pulls 16-byte pieces of its COLS weight rows (COLS independent 128-bit loads in flight per step) and keeps the
+// 16 x COLS partial sums in registers; COLS is picked by the launcher so that the grid fills the 148 SMs.
+constexpr int SKINNY_WARPS = 4;
 
-template <typename T, int ACT, bool RES>
-__global__ void __launch_bounds__(256)
+template <typename T> struct SkinnyVec;            // 16-byte vector of T
+template <> struct SkinnyVec<float> { static constexpr int N = 4; };
+template <> struct SkinnyVec<double> { static constexpr int N = 2; };
+
+template <typename T, int ACT, bool RES, int COLS>
+__global__ void __launch_bounds__(SKINNY_WARPS * 32)
 gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
                    const T* __restrict__ bias, const T* __restrict__ R, int ldr,
                    T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map) {
-  const int col0 = ((blockIdx.x * blockDim.x + threadIdx.x) / 32) * SKINNY_COLS, lane = threadIdx.x % 32;
+  extern __shared__ __align__(16) unsigned char skinny_smem[];
+  T* As = reinterpret_cast<T*>(skinny_smem);                     // [16][Kp], Kp = K rounded up to the vector width
+  constexpr int V = SkinnyVec<T>::N;
+  const int Kp = (K + V - 1) / V * V;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // staging: warp w copies rows 4w .. 4w+3; 8 independent loads in flight per lane (a dependent load -> store chain
+  // per element cost 17 us of exposed L2 latency in the first version)
+#pragma unroll
+  for (int mm = 0; mm < 16 / SKINNY_WARPS; ++mm) {
+    const int m = warp * (16 / SKINNY_WARPS) + mm;
+    const T* src = A + map(m < Mr ? m : 0) * lda;
+#pragma unroll 8
+    for (int k = lane; k < Kp; k += 32) As[m * Kp + k] = (m < Mr && k < K) ? __ldg(src + k) : T(0);
+  }
+  __syncthreads();
+  const int col0 = (blockIdx.x * SKINNY_WARPS + warp) * COLS;
   if (col0 >= Nout) return;
-  T acc[16][SKINNY_COLS];
+  T acc[16][COLS];
 #pragma unroll
   for (int m = 0; m < 16; ++m)
 #pragma unroll
-    for (int n = 0; n < SKINNY_COLS; ++n) acc[m][n] = T(0);
-  const T* arow[16];                             // row bases hoisted: RowMap costs two integer divisions
+    for (int n = 0; n < COLS; ++n) acc[m][n] = T(0);
+  const T* wrow[COLS];
 #pragma unroll
-  for (int m = 0; m < 16; ++m) arow[m] = A + map(m < Mr ? m : 0) * lda;
-  const T* wrow[SKINNY_COLS];
+  for (int n = 0; n < COLS; ++n) wrow[n] = W + (size_t)min(col0 + n, Nv - 1) * ldw;
+  // nn.Linear rows are not 16-byte aligned in general (edge_mlp.0.weight has 2*dim + 1 + ... columns), so the weight
+  // rows are read with lane-strided 4-byte (8-byte for fp64) loads: fully coalesced, V independent loads per column
+  // and step in flight; the staged activations are read with the same lane-strided pattern (conflict-free).
+  for (int k0 = 0; k0 < Kp; k0 += 32 * V) {
+    T wv[COLS][V];
 #pragma unroll
-  for (int n = 0; n < SKINNY_COLS; ++n) wrow[n] = W + (size_t)min(col0 + n, Nv - 1) * ldw;
-#pragma unroll 2
-  for (int k = lane; k < K; k += 32) {
-    T wv[SKINNY_COLS];
+    for (int n = 0; n < COLS; ++n)
 #pragma unroll
-    for (int n = 0; n < SKINNY_COLS; ++n) wv[n] = wrow[n][k];
+      for (int v = 0; v < V; ++v) {
+        const int k = k0 + v * 32 + lane;
+        wv[n][v] = k < K ? __ldg(wrow[n] + k) : T(0);
+      }
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
-      if (m < Mr) {
-        const T av = arow[m][k];
+      T av[V];
 #pragma unroll
-        for (int n = 0; n < SKINNY_COLS; ++n) acc[m][n] = fma_t(av, wv[n], acc[m][n]);
-      }
+      for (int v = 0; v < V; ++v) { const int k = k0 + v * 32 + lane; av[v] = k < Kp ? As[m * Kp + k] : T(0); }
+#pragma unroll
+      for (int n = 0; n < COLS; ++n)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[m][n] = fma_t(av[v], wv[n][v], acc[m][n]);
     }
   }
 #pragma unroll
   for (int m = 0; m < 16; ++m)
 #pragma unroll
-    for (int n = 0; n < SKINNY_COLS; ++n)
+    for (int n = 0; n < COLS; ++n)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc[m][n] += shfl_xor_t<T>(acc[m][n], o);
-  // lane = (row m, column n) for the first 16*4 = 64 results: two passes of 32 lanes
+  // every lane now holds all sums; lane l writes result number l, l + 32, ...
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    const int m = pass * 8 + lane / SKINNY_COLS, n = lane % SKINNY_COLS;
+  for (int pass = 0; pass < (16 * COLS + 31) / 32; ++pass) {
+    const int idx = pass * 32 + lane;
+    const int m = idx / COLS, n = idx % COLS;
     T v = T(0);
 #pragma unroll
     for (int mm = 0; mm < 16; ++mm)
 #pragma unroll
-      for (int nn = 0; nn < SKINNY_COLS; ++nn)
+      for (int nn = 0; nn < COLS; ++nn)
         if (mm == m && nn == n) v = acc[mm][nn];
     const int col = col0 + n;
-    if (m < Mr && col < Nout) {
+    if (idx < 16 * COLS && m < Mr && col < Nout) {
       const size_t row = map(m);
       if (col < Nv) {
         v += bias ? bias[col] : T(0);
         if (ACT == 1) v = silu_acc<T>(v);
+        if (ACT == 2) v = gelu_acc<T>(v);
         if (RES) v += R[row * ldr + col];
       } else {
         v = T(0);

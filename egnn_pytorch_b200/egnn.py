@@ -462,48 +462,103 @@ def edge_index_to_neighbors(edge_index, num_nodes, k=None):
     return out.unsqueeze(0)
 
 
-# ----------------------------------------------------------------------------- global attention (PyTorch glue)
+# ----------------------------------------------------------------------------- global attention
 
 
 class _Attention(nn.Module):
-    """Multi-head softmax attention used by GlobalLinearAttention (reference :81-110).  Outside
-    the hot path: stock PyTorch SDPA, kept for API completeness."""
+    """Parameter holder (+ autograd path) of the multi-head softmax attention inside GlobalLinearAttention
+    (reference egnn_pytorch.py:81-110): `to_q`, `to_kv` without bias, `to_out` with bias."""
 
     def __init__(self, dim, heads=8, dim_head=64):
         super().__init__()
         inner = heads * dim_head
-        self.heads = heads
+        self.heads, self.dim_head = heads, dim_head
         self.to_q = nn.Linear(dim, inner, bias=False)
         self.to_kv = nn.Linear(dim, inner * 2, bias=False)
         self.to_out = nn.Linear(inner, dim)
 
     def forward(self, x, context, mask=None):
+        """Training path (PyTorch autograd).  Masked keys get the most negative finite score BEFORE the softmax, like the
+        reference (:101-104), so a fully masked graph attends uniformly instead of producing NaN."""
         h = self.heads
         q = self.to_q(x)
         k, v = self.to_kv(context).chunk(2, dim=-1)
         split = lambda t: t.unflatten(-1, (h, -1)).transpose(1, 2)
-        attn_mask = None if mask is None else mask[:, None, None, :].to(torch.bool)
-        out = F.scaled_dot_product_attention(split(q), split(k), split(v), attn_mask=attn_mask)
+        q, k, v = split(q), split(k), split(v)
+        dots = (q @ k.transpose(-1, -2)) * self.dim_head ** -0.5
+        if mask is not None:
+            dots = dots.masked_fill(~mask[:, None, None, :].to(torch.bool), -torch.finfo(dots.dtype).max)
+        out = dots.softmax(dim=-1) @ v
         return self.to_out(out.transpose(1, 2).flatten(-2))
 
 
 class GlobalLinearAttention(nn.Module):
-    """Induced-set attention between the nodes and a few global tokens (reference :112-144)."""
+    """Induced-set attention between the nodes and a few global tokens (reference egnn_pytorch.py:112-144).
+
+    Inference (no autograd recording): ONE call of `egnn_global_attn_forward` (csrc/global_attn.cu) on staged fp32 / fp64
+    copies of the parameters -- the module itself is never moved.  When a gradient is required the same arithmetic runs
+    through PyTorch autograd (the hand-written backward of SURVEY.md section 8(f) covers the EGNN layers only)."""
 
     def __init__(self, *, dim, heads=8, dim_head=64):
         super().__init__()
+        self.dim, self.heads, self.dim_head = dim, heads, dim_head
         self.norm_seq = nn.LayerNorm(dim)
         self.norm_queries = nn.LayerNorm(dim)
         self.attn1 = _Attention(dim, heads, dim_head)
         self.attn2 = _Attention(dim, heads, dim_head)
         self.ff = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, dim * 4), nn.GELU(), nn.Linear(dim * 4, dim))
+        self._stage = {}
 
-    def forward(self, x, queries, mask=None):
+    def _forward_autograd(self, x, queries, mask=None):
         nx, nq = self.norm_seq(x), self.norm_queries(queries)
         induced = self.attn1(nq, nx, mask=mask)
         x = self.attn2(nx, induced) + x
         queries = induced + queries
         return self.ff(x) + x, queries
+
+    def _staged(self, device, dtype):
+        named = [(k, p) for k, p in self.named_parameters() if k in nat.GA_STATE_KEY_TO_FIELD]
+        sig = tuple((p.data_ptr(), p._version) for _, p in named)
+        st = self._stage.get((device, dtype))
+        if st is None or st[0] != sig:
+            with torch.no_grad():
+                tensors = {nat.GA_STATE_KEY_TO_FIELD[k]: p.detach().to(device=device, dtype=dtype).contiguous() for k, p in named}
+            w = nat.GlobalAttnWeights(**{f: t.data_ptr() for f, t in tensors.items()})
+            st = (sig, tensors, w)
+            self._stage[(device, dtype)] = st
+        return st
+
+    def invalidate_cache(self):
+        self._stage = {}
+
+    def forward(self, x, queries, mask=None):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or queries.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            dev = x.device
+            if any(p.device != dev for p in self.parameters()):
+                raise RuntimeError("training GlobalLinearAttention needs the module on the device of its inputs")
+            return self._forward_autograd(x, queries, mask)
+        lib = nat.load()
+        dev = _compute_device(x)
+        kdt = torch.float64 if x.dtype == torch.float64 else torch.float32
+        _, _, w = self._staged(dev, kdt)
+        b, n, d = x.shape
+        t = queries.shape[1]
+        x_in, q_in, m_in = _as(x, dev, kdt), _as(queries, dev, kdt), _as_u8(mask, dev)
+        x_out, q_out = torch.empty_like(x_in), torch.empty_like(q_in)
+        desc = nat.GlobalAttnDesc(abi_version=nat.ABI_VERSION, dtype=_KERNEL_DTYPE[kdt], B=b, N=n, T=t, dim=d, heads=self.heads,
+                                  dim_head=self.dim_head)
+        nb = C.c_size_t()
+        nat.check("egnn_global_attn_workspace_bytes", lib.egnn_global_attn_workspace_bytes(C.byref(desc), C.byref(nb)))
+        io = nat.GlobalAttnIO(x=x_in.data_ptr(), queries=q_in.data_ptr(), mask=None if m_in is None else m_in.data_ptr(),
+                              x_out=x_out.data_ptr(), queries_out=q_out.data_ptr())
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, nb.value)
+            nat.check("egnn_global_attn_forward",
+                      lib.egnn_global_attn_forward(C.byref(desc), C.byref(w), C.byref(io), _ptr(ws), ws.numel(),
+                                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        return x_out.to(device=x.device, dtype=x.dtype), q_out.to(device=queries.device, dtype=queries.dtype)
 
 
 # ----------------------------------------------------------------------------- the network
@@ -600,7 +655,6 @@ class EGNN_Network(nn.Module):
         coor_changes = [coors]
         for global_attn, egnn in self.layers:
             if exists(global_attn):
-                global_attn = global_attn.to(dev)
                 feats, global_tokens = global_attn(feats, global_tokens, mask=mask)
             feats, coors = egnn(feats, coors, edges, mask, adj_mat, _edge_labels=labels, _label_emb=label_emb,
                                 _k_hint=k_hint)

@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define EGNN_ABI_VERSION 3   /* 2: EgnnLayerIO grew nbr_idx + pre2_out; backward entry points added
-                                3: peer-memory all-gather communicator (egnn_comm_*) */
+                                3: peer-memory all-gather communicator (egnn_comm_*), egnn_global_attn_* */
 
 /* ---- error codes ------------------------------------------------------------------- */
 #define EGNN_OK                 0
@@ -215,6 +215,42 @@ int egnn_adj_expand(int32_t B, int32_t N, int32_t num_degrees, const uint8_t* ad
  * act 0 = none / 1 = SiLU, out fp32 (out_f32 = 1) or bf16. */
 int egnn_gemm_bf16(int32_t M, int32_t N, int32_t K, const void* A, const void* W, const float* bias,
                    float scale, int32_t act, void* out, int32_t out_f32, void* stream);
+
+/*
+ * GlobalLinearAttention of EGNN_Network (reference egnn_pytorch.py:81-144, applied between layers at :445-446): the
+ * T global tokens attend over the (masked) nodes, the nodes attend over the induced tokens, residuals, pre-norm GELU
+ * feed-forward.  Forward only, fp32 / fp64 (a bf16 module passes fp32 copies).  Weights exactly as the reference's
+ * state dict stores them (row-major [out, in]); all pointers device memory, contiguous.
+ */
+typedef struct EgnnGlobalAttnDesc {
+  int32_t abi_version;    /* EGNN_ABI_VERSION */
+  int32_t dtype;          /* EGNN_DTYPE_F32 | EGNN_DTYPE_F64 */
+  int32_t B, N, T;        /* graphs, nodes, global tokens (T <= 32) */
+  int32_t dim, heads, dim_head;
+} EgnnGlobalAttnDesc;
+
+typedef struct EgnnGlobalAttnWeights {
+  const void* norm_seq_g; const void* norm_seq_b;      /* [dim]  norm_seq.weight / .bias        */
+  const void* norm_q_g;   const void* norm_q_b;        /* [dim]  norm_queries.weight / .bias    */
+  const void* a1_wq;  const void* a1_wkv;              /* [inner, dim], [2 inner, dim]  attn1.to_q / to_kv.weight (inner = heads * dim_head) */
+  const void* a1_wo;  const void* a1_bo;               /* [dim, inner], [dim]           attn1.to_out.weight / .bias */
+  const void* a2_wq;  const void* a2_wkv; const void* a2_wo; const void* a2_bo;   /* attn2, same shapes */
+  const void* ff_ln_g; const void* ff_ln_b;            /* [dim]          ff.0.weight / .bias    */
+  const void* ff_w1;  const void* ff_b1;               /* [4 dim, dim], [4 dim]   ff.1          */
+  const void* ff_w2;  const void* ff_b2;               /* [dim, 4 dim], [dim]     ff.3          */
+} EgnnGlobalAttnWeights;
+
+typedef struct EgnnGlobalAttnIO {
+  const void*    x;            /* [B, N, dim] node features                         */
+  const void*    queries;      /* [B, T, dim] global tokens                         */
+  const uint8_t* mask;         /* [B, N] 0/1 or NULL; a fully masked graph attends uniformly (:101-104) */
+  void*          x_out;        /* [B, N, dim]                                       */
+  void*          queries_out;  /* [B, T, dim]                                       */
+} EgnnGlobalAttnIO;
+
+int egnn_global_attn_workspace_bytes(const EgnnGlobalAttnDesc* desc, size_t* out_bytes);
+int egnn_global_attn_forward(const EgnnGlobalAttnDesc* desc, const EgnnGlobalAttnWeights* w, const EgnnGlobalAttnIO* io,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Peer-memory all-gather over NVLink for the ROW-SHARDED single graph (reference

@@ -315,21 +315,67 @@ def egnn_layer_forward_edge_list(params, cfg, feats, coors, neighbors, edges=Non
 
 
 def network_cfg(*, depth, dim, num_tokens=None, num_edge_tokens=None, num_positions=None,
-                edge_dim=0, num_adj_degrees=None, adj_dim=0, **egnn_kwargs):
-    """Keyword set of `EGNN_Network.__init__` (egnn_pytorch.py:344-388).  Global linear
-    attention (off by default) is outside the hot path and is not
-    restated; the oracle refuses it."""
-    for k in list(egnn_kwargs):
-        if k.startswith("global_linear_attn") or k == "num_global_tokens":
-            assert not egnn_kwargs[k] or k != "global_linear_attn_every", "global attention not restated"
-            egnn_kwargs.pop(k)
+                edge_dim=0, num_adj_degrees=None, adj_dim=0, global_linear_attn_every=0,
+                global_linear_attn_heads=8, global_linear_attn_dim_head=64, num_global_tokens=4, **egnn_kwargs):
+    """Keyword set of `EGNN_Network.__init__` (egnn_pytorch.py:344-388)."""
     assert not (num_adj_degrees is not None and num_adj_degrees < 1)               # :362
     has_edges = edge_dim > 0
     layer_edge = (edge_dim if has_edges else 0) + (adj_dim if num_adj_degrees is not None else 0)   # :372-373, :387
+    every = global_linear_attn_every
     return dict(depth=depth, dim=dim, num_tokens=num_tokens, num_edge_tokens=num_edge_tokens,
                 num_positions=num_positions, edge_dim=edge_dim, num_adj_degrees=num_adj_degrees,
                 adj_dim=adj_dim,
+                global_every=every, global_heads=global_linear_attn_heads, global_dim_head=global_linear_attn_dim_head,
+                num_global_tokens=num_global_tokens,
+                global_layers=[l for l in range(depth) if every > 0 and l % every == 0],            # :381-382
                 layer=layer_cfg(dim=dim, edge_dim=layer_edge, norm_feats=True, **egnn_kwargs))
+
+
+def gelu(x):
+    """nn.GELU() (exact, erf form), egnn_pytorch.py:127."""
+    from math import sqrt
+    try:
+        from scipy.special import erf
+    except Exception:       # pragma: no cover
+        erf = np.vectorize(__import__("math").erf)
+    return 0.5 * x * (1.0 + erf(x / sqrt(2.0)))
+
+
+def attention(P, prefix, x, context, heads, mask=None):
+    """`Attention.forward` (egnn_pytorch.py:92-110): softmax(q k^T * dim_head^-0.5) v over `context`, heads split from
+    the channel axis, masked keys filled with -finfo.max BEFORE the softmax (so a fully masked row is uniform)."""
+    q = linear(x, P[prefix + "to_q.weight"])                                        # :95
+    kv = linear(context, P[prefix + "to_kv.weight"])                                # :96
+    inner = q.shape[-1]
+    k, v = kv[..., :inner], kv[..., inner:]
+    b, n = q.shape[:2]
+    j = k.shape[1]
+    dh = inner // heads
+    split = lambda t_, m: t_.reshape(b, m, heads, dh).transpose(0, 2, 1, 3)        # b n (h d) -> b h n d, :98
+    q, k, v = split(q, n), split(k, j), split(v, j)
+    dots = np.einsum("bhid,bhjd->bhij", q, k) * dh ** -0.5                          # :99
+    if mask is not None:
+        dots = np.where(np.asarray(mask).astype(bool)[:, None, None, :], dots, -np.finfo(dots.dtype).max)   # :101-104
+    dots = dots - dots.max(-1, keepdims=True)
+    attn = np.exp(dots)
+    attn = attn / attn.sum(-1, keepdims=True)                                       # :106
+    out = np.einsum("bhij,bhjd->bhid", attn, v).transpose(0, 2, 1, 3).reshape(b, n, inner)   # :107-109
+    return linear(out, P[prefix + "to_out.weight"], P[prefix + "to_out.bias"])     # :110
+
+
+def global_linear_attention(P, prefix, x, queries, heads, mask=None):
+    """`GlobalLinearAttention.forward` (egnn_pytorch.py:132-144): the global tokens attend over the (masked) nodes, the
+    nodes attend over the induced tokens, residuals, then a pre-norm GELU feed-forward on the nodes."""
+    res_x, res_q = x, queries
+    xn = layer_norm(x, P[prefix + "norm_seq.weight"], P[prefix + "norm_seq.bias"])
+    qn = layer_norm(queries, P[prefix + "norm_queries.weight"], P[prefix + "norm_queries.bias"])
+    induced = attention(P, prefix + "attn1.", qn, xn, heads, mask)                  # :136
+    out = attention(P, prefix + "attn2.", xn, induced, heads)                       # :137
+    x = out + res_x                                                                 # :139
+    queries = induced + res_q                                                       # :140
+    y = layer_norm(x, P[prefix + "ff.0.weight"], P[prefix + "ff.0.bias"])
+    y = linear(gelu(linear(y, P[prefix + "ff.1.weight"], P[prefix + "ff.1.bias"])), P[prefix + "ff.3.weight"], P[prefix + "ff.3.bias"])
+    return y + x, queries                                                           # :142-143
 
 
 def adjacency_degrees(adj_mat, num_adj_degrees, b):
@@ -354,7 +400,7 @@ def adjacency_degrees(adj_mat, num_adj_degrees, b):
 
 def egnn_network_forward(params, cfg, feats, coors, adj_mat=None, edges=None, mask=None,
                          return_coor_changes=False, dtype=np.float64, row_chunk=64):
-    """`EGNN_Network.forward`, egnn_pytorch.py:390-454 (without global attention)."""
+    """`EGNN_Network.forward`, egnn_pytorch.py:390-454."""
     P = params
     coors = np.asarray(coors, dtype=dtype)
     b = np.asarray(feats).shape[0]
@@ -375,8 +421,14 @@ def egnn_network_forward(params, cfg, feats, coors, adj_mat=None, edges=None, ma
             adj_emb = np.asarray(P["adj_emb.weight"], dtype=dtype)[labels]          # :430-431
             edges = adj_emb if edges is None else np.concatenate(
                 [np.asarray(edges, dtype=dtype), adj_emb], axis=-1)                 # :432
+    global_tokens = None
+    if cfg.get("global_layers"):
+        global_tokens = np.broadcast_to(np.asarray(P["global_tokens"], dtype=dtype), (b,) + np.shape(P["global_tokens"]))   # :439-440
     coor_changes = [coors]
     for l in range(cfg["depth"]):
+        if l in cfg.get("global_layers", []):                                       # :445-446
+            PD = {k: np.asarray(v, dtype=dtype) for k, v in P.items() if k.startswith(f"layers.{l}.0.")}
+            feats, global_tokens = global_linear_attention(PD, f"layers.{l}.0.", feats, global_tokens, cfg["global_heads"], mask)
         prefix = f"layers.{l}.1."
         lp = {k[len(prefix):]: v for k, v in P.items() if k.startswith(prefix)}
         feats, coors = egnn_layer_forward(lp, cfg["layer"], feats, coors, edges=edges, mask=mask,

@@ -89,6 +89,26 @@ def gen_network_params(ncfg, rs, init):
     for l in range(ncfg["depth"]):
         for k, v in gen_layer_params(ncfg["layer"], rs, init).items():
             out[f"layers.{l}.1.{k}"] = v
+    # global linear attention blocks (reference egnn_pytorch.py:112-130), generated AFTER everything else so that the
+    # parameter streams of the cases without them are unchanged
+    if ncfg.get("global_layers"):
+        inner = ncfg["global_heads"] * ncfg["global_dim_head"]
+        out["global_tokens"] = rs.standard_normal((ncfg["num_global_tokens"], d))
+        lin = lambda o, i: rs.standard_normal((o, i)) * math.sqrt(1.0 / i)
+        for l in ncfg["global_layers"]:
+            pre = f"layers.{l}.0."
+            for nm in ("norm_seq", "norm_queries", "ff.0"):
+                out[pre + nm + ".weight"] = 1.0 + 0.2 * rs.standard_normal((d,))
+                out[pre + nm + ".bias"] = 0.1 * rs.standard_normal((d,))
+            for a in ("attn1", "attn2"):
+                out[pre + a + ".to_q.weight"] = lin(inner, d)
+                out[pre + a + ".to_kv.weight"] = lin(2 * inner, d)
+                out[pre + a + ".to_out.weight"] = lin(d, inner)
+                out[pre + a + ".to_out.bias"] = 0.1 * rs.standard_normal((d,))
+            out[pre + "ff.1.weight"] = lin(4 * d, d)
+            out[pre + "ff.1.bias"] = 0.1 * rs.standard_normal((4 * d,))
+            out[pre + "ff.3.weight"] = lin(d, 4 * d)
+            out[pre + "ff.3.bias"] = 0.1 * rs.standard_normal((d,))
     return out
 
 
@@ -135,6 +155,10 @@ def gen_inputs(spec, rs):
     elif mk == "random":
         m = rs.uniform(size=(B, N)) < 0.8
         m[:, :2] = True
+        ins["mask"] = m
+    elif mk == "one_empty":   # the last graph of the batch has no valid node at all
+        m = np.ones((B, N), bool)
+        m[-1] = False
         ins["mask"] = m
     adj = spec.get("adj", "none")
     if adj == "chain":
@@ -264,6 +288,16 @@ SPECS = {
                                init="xavier", adj="chain", mask="padded"),   # degree labels on DENSE layers (no neighbour selection)
     "net_adj_random":     dict(kind=NW, cfg=dict(depth=2, dim=12, num_adj_degrees=2, adj_dim=3, only_sparse_neighbors=True),
                                B=2, N=16, seed=57, init="xavier", adj="random3d", adj_p=0.1, mask="full"),
+    # EGNN_Network with GlobalLinearAttention blocks (reference egnn_pytorch.py:81-144, :381-385, :439-446)
+    "net_global_attn":    dict(kind=NW, cfg=dict(depth=2, dim=16, num_tokens=9, global_linear_attn_every=1, global_linear_attn_heads=2,
+                                                 global_linear_attn_dim_head=8, num_global_tokens=3), B=2, N=14, seed=59,
+                               init="xavier", mask="padded"),
+    "net_global_every2":  dict(kind=NW, cfg=dict(depth=3, dim=24, global_linear_attn_every=2, global_linear_attn_heads=4,
+                                                 global_linear_attn_dim_head=16, num_global_tokens=4, num_nearest_neighbors=5,
+                                                 norm_coors=True), B=2, N=20, seed=60, init="xavier"),
+    "net_global_allmask": dict(kind=NW, cfg=dict(depth=1, dim=16, global_linear_attn_every=1, global_linear_attn_heads=2,
+                                                 global_linear_attn_dim_head=8, num_global_tokens=2), B=2, N=9, seed=61,
+                               init="xavier", mask="one_empty"),     # one graph fully masked: uniform attention (:101-104)
 }
 
 
@@ -273,7 +307,8 @@ SPECS = {
 # backward pass exercises every output element.  The huge-parameter c1 cases are left out of the committed
 # gradient fixtures (25 MB each in float64); they are still checked CUDA-vs-oracle.
 
-GRAD_SPECS = [n for n in SPECS if not n.startswith("c1_") and n not in {"knn_k33", "knn_k32_c5"}]
+# (the global-attention blocks train through PyTorch autograd, not through egnn_layer_backward: no hand-written gradient)
+GRAD_SPECS = [n for n in SPECS if not n.startswith("c1_") and not n.startswith("net_global") and n not in {"knn_k33", "knn_k32_c5"}]
 
 
 def upstream_grads(case):

@@ -75,6 +75,9 @@ FAST_SPECS = {
     "net_c5_xavier":   dict(kind="network", cfg=dict(depth=2, dim=32, num_tokens=21, num_adj_degrees=2, adj_dim=4, edge_dim=2,
                                                      num_edge_tokens=4, only_sparse_neighbors=True), B=2, N=40, seed=64, init="xavier",
                             adj="chain", edges=True, mask="padded"),
+    "net_global_bf16": dict(kind="network", cfg=dict(depth=2, dim=32, num_tokens=9, global_linear_attn_every=1, global_linear_attn_heads=2,
+                                                     global_linear_attn_dim_head=16, num_global_tokens=3), B=2, N=24, seed=66,
+                            init="xavier", mask="padded"),      # attention block in fp32 between bf16 tensor-core layers
     # depth 1: with more layers the bf16 coordinate round-off of layer 1 may flip a near-tie of layer 2's top-k, which is a
     # property of re-selecting neighbours, not of the kernels (the full c3 shape is covered in test_gpu_baseline_configs)
     "net_c3_like":     dict(kind="network", cfg=dict(depth=1, dim=32, num_tokens=21, num_positions=128, num_nearest_neighbors=8,
