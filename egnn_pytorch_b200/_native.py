@@ -26,7 +26,7 @@ FLAG_ADJ_BATCHED = 1 << 8
 ERR_UNSUPPORTED = -3
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libegnn_b200.so")
+LIB_PATH = os.environ.get("EGNN_B200_LIB") or os.path.join(LIB_DIR, "libegnn_b200.so")   # override: A/B runs of kernel variants
 
 
 class LayerDesc(C.Structure):

@@ -260,11 +260,17 @@ uint32_t pair_skew_ns() {
   return v;
 }
 
-int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st) {
+// one launch for one (g2 == nullptr) or two problems over the same rows
+int launch_tc_gemm(const TcGemmArgs& g, cudaStream_t st, const TcGemmArgs* g2 = nullptr) {
   if (g.M <= 0) return EGNN_OK;
   EGNN_TRY((ensure_dyn_smem<0>(tc_gemm_kernel, GEMM_SMEM_BYTES)));
-  dim3 grid(ceil_div(g.Nout, GEMM_BN), ceil_div(g.M, GEMM_BM));
-  tc_gemm_kernel<<<grid, 128, GEMM_SMEM_BYTES, st>>>(g);
+  TcGemmPair gp;
+  gp.p[0] = g;
+  gp.p[1] = g2 ? *g2 : g;
+  gp.nt0 = ceil_div(g.Nout, GEMM_BN);
+  const int nt1 = g2 ? ceil_div(g2->Nout, GEMM_BN) : 0;
+  dim3 grid(gp.nt0 + nt1, ceil_div(g.M, GEMM_BM));
+  tc_gemm_kernel<<<grid, 128, GEMM_SMEM_BYTES, st>>>(gp);
   EGNN_LAUNCH_CHECK();
   count_launch();
   return EGNN_OK;
@@ -338,14 +344,20 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1i); g.ldw = s.dim;
     g.bias = reinterpret_cast<const float*>(pk + L.b1);
     g.out_f32 = 1;
-    for (int sg = 0; sg < nseg; ++sg) {
-      g.A = feats + seg_begin(sg) * s.dim; g.M = seg_rows; g.out = Atab + seg_begin(sg) * f.Hp;
-      EGNN_TRY(launch_tc_gemm(g, st));
+    TcGemmArgs gb = g;                                    // B' = 0.5 h W1_j^T over ALL rows
+    gb.A = feats; gb.M = s.M;
+    gb.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j); gb.bias = nullptr;
+    gb.out = Btab; gb.out_f32 = 0;
+    if (all_rows) {                                       // both tables in one launch (same rows, same activations)
+      g.A = feats; g.M = s.M; g.out = Atab;
+      EGNN_TRY(launch_tc_gemm(g, st, &gb));
+    } else {
+      for (int sg = 0; sg < nseg; ++sg) {
+        g.A = feats + seg_begin(sg) * s.dim; g.M = seg_rows; g.out = Atab + seg_begin(sg) * f.Hp;
+        EGNN_TRY(launch_tc_gemm(g, st));
+      }
+      EGNN_TRY(launch_tc_gemm(gb, st));
     }
-    g.A = feats; g.M = s.M;
-    g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j); g.bias = nullptr;
-    g.out = Btab; g.out_f32 = 0;
-    EGNN_TRY(launch_tc_gemm(g, st));
   }
   if (s.k == 0) {  // fused edge kernel, dense all-pairs (persistent: one CTA per SM walks the row groups)
     StageTimer tm(st, STAGE_PAIR);

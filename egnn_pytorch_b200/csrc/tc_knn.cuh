@@ -234,18 +234,24 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   };
 
   const float* Arow = As + (size_t)warp * Hp + lq * 4;
-#pragma unroll 1
-  for (int c = 0; c < nchunks; ++c) {
+  // chunks with all 4 K slabs run with NSLC = 4 (the slab tests fold at compile time); only the last chunk of a hidden
+  // width that is not a multiple of 64 takes the predicated instantiation (NSLC = 0)
+  auto chunk = [&](const int c, auto nslc) {
+    constexpr int NSLC = decltype(nslc)::value;
     const uint32_t slot = (uint32_t)c % TK_SLOTS;
     const uint32_t ta = tm_wg + 16 + slot * 32;
-    const bool more = c + 1 < nchunks;
-    const int nsl = c + 1 == nchunks ? nsl_last : 4, nsl_next = c + 2 == nchunks ? nsl_last : 4;
+    const bool more = NSLC != 0 && c + 1 < nchunks;
+    const int nsl = NSLC ? NSLC : nsl_last, nsl_next = c + 2 == nchunks ? nsl_last : 4;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       uint32_t hp[16];
 #pragma unroll
       for (int sl = 0; sl < 4; ++sl) {
-        const bool slv = sl < nsl;                          // slabs beyond Hp (last chunk only): zeros, never multiplied
+        if (NSLC == 0 && sl >= nsl) {                       // tail chunk: slabs beyond H are not computed (no MUFU work)
+          hp[sl * 4 + 0] = hp[sl * 4 + 1] = hp[sl * 4 + 2] = hp[sl * 4 + 3] = 0u;
+          continue;
+        }
+        const bool slv = sl < nsl;                          // (always true here; kept for the loads below)
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 av = slv ? *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16) : zero4;
         const float4 wv = (slv && !GEN) ? *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4) : zero4;
@@ -302,6 +308,12 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     tc::tc_fence_before();
     tc::mbar_arrive(&full[g * TK_SLOTS + slot]);
     pend_c = c;
+  };
+  {
+    const int nfull = nsl_last == 4 ? nchunks : nchunks - 1;
+#pragma unroll 1
+    for (int c = 0; c < nfull; ++c) chunk(c, tc::IntC<4>{});
+    if (nfull < nchunks) chunk(nchunks - 1, tc::IntC<0>{});
   }
   issue_pending();
 

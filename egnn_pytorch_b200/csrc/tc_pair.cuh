@@ -49,6 +49,10 @@
 
 namespace egnn {
 
+#ifndef EPI_UNROLL
+#define EPI_UNROLL 2
+#endif
+constexpr int TP_EPI_UNROLL = EPI_UNROLL;
 constexpr int TP_TI = 4;          // query rows per row group
 constexpr int TP_KC = 64;         // hidden channels per chunk (= 32 TMEM columns, 4 MMAs)
 constexpr int TP_SLOTS = 2;       // A-operand slots per warpgroup
@@ -218,6 +222,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
     __nv_bfloat16* shg = ssh + (size_t)g * Qh * TP_TI * 128;
     constexpr uint32_t IDESC = tc::idesc_bf16_f32(128, 16);
     const uint32_t w2a = tc::smem_u32(w2s);           // W2 slab s at +512*s: K-adjacent core matrices 256 B apart, N-adjacent 128 B
+    const uint32_t full_a = tc::smem_u32(&full[g * TP_SLOTS]), empty_a = tc::smem_u32(&empty[g * TP_SLOTS]);   // + 8 * slot
+    const uint32_t accdone_a = tc::smem_u32(&accdone[g]);
     if (a.skew_ns && g > 0) {                         // de-phase the warpgroups (see the header)
       uint64_t t0, t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           pend_valid = false;
           if ((pend_n & 3u) != (uint32_t)wq) return;      // rotating duty: warp (round % 4) of the warpgroup issues
           const uint32_t pslot = pend_n & (TP_SLOTS - 1);
-          tc::mbar_wait(&full[g * TP_SLOTS + pslot], (pend_n / TP_SLOTS) & 1);
+          tc::mbar_wait_a(full_a + 8 * pslot, (pend_n / TP_SLOTS) & 1);
           tc::tc_fence_after();
           if (lane == 0) {
             const uint32_t tm_g = tmem + g * TP_WGCOLS;
@@ -314,8 +320,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
                 tc::mma_ts(tm_g + pend_i * 16, tm_g + TP_TI * 16 + pslot * 32 + kk * 8, bd, IDESC, (pend_c > 0 || kk > 0) ? 1u : 0u);
               }
             }
-            tc::mma_commit(&empty[g * TP_SLOTS + pslot]);
-            if (pend_c + 1 == nchunks && pend_i + 1 == TP_TI) tc::mma_commit(&accdone[g]);
+            tc::mma_commit_a(empty_a + 8 * pslot);
+            if (pend_c + 1 == nchunks && pend_i + 1 == TP_TI) tc::mma_commit_a(accdone_a);
           }
           __syncwarp();
         };
@@ -392,6 +398,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
               uint32_t hp[16];
 #pragma unroll
               for (int sl = 0; sl < 4; ++sl) {
+                if (NSLC == 0 && sl >= nsl) {              // tail chunk: slabs beyond H are not computed (no MUFU work) ...
+                  hp[sl * 4 + 0] = hp[sl * 4 + 1] = hp[sl * 4 + 2] = hp[sl * 4 + 3] = 0u;     // ... and never multiplied
+                  continue;
+                }
 #pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {
                   const int rho = half * 2 + r2;
@@ -418,14 +428,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
               }
               if (half == 0) {
                 issue_pending();                          // round n-1's MMAs, if this warp has the duty
-                tc::mbar_wait(&empty[g * TP_SLOTS + slot], ((n / TP_SLOTS) & 1) ^ 1);
+                tc::mbar_wait_a(empty_a + 8 * slot, ((n / TP_SLOTS) & 1) ^ 1);
                 tc::tc_fence_after();
               }
               tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
             }
             tc::tmem_wait_st();
             tc::tc_fence_before();
-            tc::mbar_arrive(&full[g * TP_SLOTS + slot]);
+            tc::mbar_arrive_a(full_a + 8 * slot);
             pend_c = c; pend_i = i; pend_n = n; pend_valid = true;
             ++n;
           };
@@ -448,7 +458,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         issue_pending();                                  // last round of the tile: also signals accdone
 
         // ---- epilogue of this tile: accumulators back to the owning thread (pair mapping)
-        tc::mbar_wait(&accdone[g], tl & 1);
+        tc::mbar_wait_a(accdone_a, tl & 1);
         ++tl;
         tc::tc_fence_after();
         const float* W3 = epi; const float* b3 = epi + 1024; const float* w4 = b3 + 64;
@@ -476,8 +486,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         for (int i = 0; i < TP_TI; ++i) wgt[i] = 0.f;
         if (upd_coors) {                                                                                      // :302-315
           // hidden unit u outermost: one W3 row (4 x LDS.128) serves all TI rows of this pair; the four rows are four
-          // independent FMA chains (packing them two by two as FFMA2 halves the chains in flight and measured 2.5 % slower)
-#pragma unroll 2
+          // independent FMA chains (same-box A/B, tools/ab_variants.sh: packing them two by two as FFMA2 is 1.4 % SLOWER
+          // on the whole kernel -- it halves the chains in flight and FFMA2 has no higher FMA throughput)
+#pragma unroll TP_EPI_UNROLL
           for (int u = 0; u < 64; ++u) {
             const float4* w3 = reinterpret_cast<const float4*>(W3 + u * 16);
             const float4 wa = w3[0], wb = w3[1], wc = w3[2], wd4 = w3[3];

@@ -1,0 +1,12 @@
+#!/bin/bash
+# same-box A/B of kernel variants: EGNN_B200_LIB selects the shared library; variants interleaved, REPS repetitions
+set -u
+mkdir -p gpurun_out
+for rep in $(seq 1 ${REPS:-3}); do
+  for v in egnn_pytorch_b200/lib/variants/*.so; do
+    EGNN_B200_LIB=$PWD/$v timeout 300 python bench.py --dtype bf16 --steps 20 --warmup 5 --lean 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('rep $rep %-18s ms/step %.4f edge %.4f pre %.4f post %.4f' % ('$(basename $v)', d['ms_per_step'], r['launch_ms'], r['stage_ms_per_step']['node_pre'], r['stage_ms_per_step']['node_post']))"
+  done
+done
