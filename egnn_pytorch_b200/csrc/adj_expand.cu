@@ -122,3 +122,51 @@ extern "C" int egnn_adj_expand(int32_t B, int32_t N, int32_t num_degrees, const 
   EGNN_LAUNCH_CHECK();
   return EGNN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Node embedding of EGNN_Network (reference egnn_pytorch.py:401-408) in one launch:
+//     feats[b, n, :] = token_emb[tokens[b, n], :] (+ pos_emb[n, :])
+// (the reference runs nn.Embedding, an arange + nn.Embedding for the positions and an in-place add).  Element type T for
+// tables and output; tokens int64.  One warp per node row.
+namespace egnn {
+template <typename T>
+__global__ void embed_nodes_kernel(const int64_t* __restrict__ tokens, const T* __restrict__ tok_emb, const T* __restrict__ pos_emb,
+                                   T* __restrict__ out, int B, int N, int dim, int num_tokens) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= (size_t)B * N) return;
+  const int n = (int)(row % N);
+  long long t = tokens[row];
+  t = t < 0 ? 0 : (t >= num_tokens ? num_tokens - 1 : t);            // nn.Embedding would raise; never read out of bounds
+  const T* te = tok_emb + (size_t)t * dim;
+  const T* pe = pos_emb ? pos_emb + (size_t)n * dim : nullptr;
+  for (int c = lane; c < dim; c += 32) {
+    if constexpr (sizeof(T) == 2) {
+      const float v = __bfloat162float(te[c]) + (pe ? __bfloat162float(pe[c]) : 0.f);     // one rounding, like bf16 add
+      out[row * dim + c] = __float2bfloat16(v);
+    } else {
+      out[row * dim + c] = te[c] + (pe ? pe[c] : T(0));
+    }
+  }
+}
+}  // namespace egnn
+
+extern "C" int egnn_embed_nodes(int32_t dtype, int32_t B, int32_t N, int32_t dim, int32_t num_tokens, const int64_t* tokens,
+                                const void* token_emb, const void* pos_emb, void* out, void* stream) {
+  if (!tokens || !token_emb || !out) return EGNN_ERR_NULL;
+  if (B <= 0 || N <= 0 || dim <= 0 || num_tokens <= 0) return EGNN_ERR_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)(((size_t)B * N * 32 + 255) / 256);
+  if (dtype == EGNN_DTYPE_F64)
+    egnn::embed_nodes_kernel<double><<<grid, 256, 0, st>>>(tokens, static_cast<const double*>(token_emb), static_cast<const double*>(pos_emb),
+                                                           static_cast<double*>(out), B, N, dim, num_tokens);
+  else if (dtype == EGNN_DTYPE_F32)
+    egnn::embed_nodes_kernel<float><<<grid, 256, 0, st>>>(tokens, static_cast<const float*>(token_emb), static_cast<const float*>(pos_emb),
+                                                          static_cast<float*>(out), B, N, dim, num_tokens);
+  else
+    egnn::embed_nodes_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(tokens, static_cast<const __nv_bfloat16*>(token_emb),
+                                                                  static_cast<const __nv_bfloat16*>(pos_emb),
+                                                                  static_cast<__nv_bfloat16*>(out), B, N, dim, num_tokens);
+  EGNN_LAUNCH_CHECK();
+  return EGNN_OK;
+}

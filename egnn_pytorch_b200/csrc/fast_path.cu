@@ -202,7 +202,8 @@ __global__ void ln_concat_bf16_kernel(const __nv_bfloat16* __restrict__ h, const
   for (int c = lane; c < dim; c += 32) y[c] = __float2bfloat16((__bfloat162float(x[c]) - mu) * rstd * g[c] + bta[c]);
 }
 
-struct FastWs { size_t Atab, Btab, node_in, h1, nbr_idx, nbr_ok, total; };
+struct FastWs { size_t Atab, Btab, node_in, h1, nbr_idx, nbr_ok, gpart, gcount, total; };
+constexpr int TP_JSPLIT_MAX = 8;
 FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   FastWs w;
   size_t o = 0;
@@ -214,6 +215,10 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   w.h1 = take(uf ? (size_t)f.s.M * 2 * f.s.dim * 2 : 0);
   w.nbr_idx = take((size_t)f.s.M * f.s.k * sizeof(int32_t));
   w.nbr_ok = take((size_t)f.s.M * f.s.k);
+  // dense kernel, j-split mode: partial sums and arrival counters per row group (the counters are kept zero between calls)
+  const size_t rgs = f.s.k == 0 ? (size_t)f.s.B * ceil_div(f.s.row1 - f.s.row0, TP_TI) : 0;
+  w.gpart = take(rgs * TP_JSPLIT_MAX * TP_TI * TpCfg<true>::PW * 8);
+  w.gcount = take(rgs * 4);
   w.total = o;
   return w;
 }
@@ -381,8 +386,21 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     if (s.edge_dim > 0 && !io.edges) return EGNN_ERR_NULL;
     int sms = 0;
     EGNN_TRY(sm_count(&sms));
-    const int items = s.B * ceil_div(R, TP_TI);
+    int items = s.B * ceil_div(R, TP_TI);
     if (items > 0) {
+      // too few row groups to balance one CTA per SM: deal the j-blocks of every row group to 2 / 4 / 8 items
+      const int njb = ceil_div(s.N, TP_JB);
+      int js = 1;
+      while (js < TP_JSPLIT_MAX && items * js < 6 * sms && js * 2 <= njb) js *= 2;
+      a.jsplit = js;
+      a.gpart = reinterpret_cast<double*>(base + wl.gpart);
+      a.gcount = reinterpret_cast<unsigned int*>(base + wl.gcount);
+      if (js > 1) {
+        // the counters must be zero on entry; the kernel leaves them zero, so only a workspace that was never used in
+        // this mode (or was used for something else) needs the memset -- it is cheap enough to do always
+        EGNN_CUDA_TRY(cudaMemsetAsync(a.gcount, 0, (size_t)items * 4, st));
+        items *= js;
+      }
       const int grid = items < sms ? items : sms;
       if (items < 2 * sms) a.skew_ns = 0;                      // too few row groups per CTA for the de-phasing to pay
       if (pair_is_lean(f)) {

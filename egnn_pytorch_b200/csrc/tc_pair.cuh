@@ -72,6 +72,9 @@ struct TcPairArgs {
   int row0, row1;                  // i-rows [row0, row1) of every graph are evaluated (row-sharded multi-GPU)
   uint32_t flags; int has_mask; float clamp;
   uint32_t skew_ns;                // start-up delay between consecutive warpgroups
+  int jsplit;                      // j-blocks of a row group are dealt to `jsplit` work items (1 = one item per row group)
+  double* gpart;                   // [B * row groups][jsplit][TI][PW] partial sums of the items (jsplit > 1)
+  unsigned int* gcount;            // [B * row groups] arrival counters, zero on entry and on exit (jsplit > 1)
   const float* Atab;               // [M][Hp]  0.5 (h W1_i^T + b1)
   const __nv_bfloat16* Btab;       // [M][Hp]  0.5 h W1_j^T
   const float* wq;                 // [Q][Hp]  0.5 * per-pair scalar columns of W1: d | sin | cos | edges | label table
@@ -101,7 +104,7 @@ inline size_t tc_pair_smem_bytes(int Hp, int Q, int Qf = 1) {
   n += (size_t)Q * Hp * 4;                                  // Wq
   n += (size_t)2 * TP_TI * Hp * 4;                          // A' rows, two-deep ring
   n += (size_t)TP_EPI_FLOATS * 4;                           // epilogue constants
-  n += (size_t)2 * TP_CWARPS * TP_TI * TpCfg<GEN>::PW * 4;  // per-warp partial sums, per ring slot
+  n += (size_t)2 * TP_CWARPS * TP_TI * TpCfg<GEN>::PW * 8;  // per-warp partial sums (fp64), per ring slot
   n += (size_t)2 * TP_TI * TpCfg<GEN>::XC * 4 + 2 * TP_TI * 4 + 64;   // x_i, mask_i per ring slot; counters, tmem pointer
   n += (size_t)(GEN ? 0 : 1) * TP_TI * TP_JB * 4;           // lean: d_ij of the current tiles
   (void)Q;
@@ -112,6 +115,74 @@ inline size_t tc_pair_smem_bytes(int Hp, int Q, int Qf = 1) {
 
 // named barrier over one warpgroup (ids 1..4; id 0 is __syncthreads)
 __device__ __forceinline__ void tp_wg_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+// End of a work item, run by the LAST warpgroup of the CTA to finish it (kept out of line: its registers must not add to the
+// pressure of the round loop).  jsplit == 1: add the 16 warps' partial sums and write m_i / x_i'.  jsplit > 1: publish this
+// item's sums; the last of the row group's items (device-scope counter) adds the parts in order and writes the outputs.
+struct TpFinishArgs {               // the fields of TcPairArgs the finish needs, passed BY VALUE (a reference to the kernel
+  int jsplit, N, C, ldn, has_mask;  // parameter block would force a local-memory copy of all of it)
+  uint32_t flags;
+  double* gpart; unsigned int* gcount; __nv_bfloat16* m_out; float* coors_out;
+};
+template <bool GEN>
+__device__ __noinline__ void tp_finish_item(const TpFinishArgs a, const double* partb, uint32_t* misc, const float* xi, int item, int b,
+                                            int i0, int rows_valid, int active_wgs, int g, int t128) {
+  constexpr int PW = TpCfg<GEN>::PW, XC = TpCfg<GEN>::XC;
+  const int N = a.N, C = a.C;
+  const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
+        const int S = a.jsplit;
+        const int rgid = item / S;                         // global row-group index
+        bool finish = true;                                // does this item write the row group's outputs?
+        if (S > 1) {
+          // publish this item's sums, then find out whether it is the last of the row group's S items
+          if (t128 < TP_TI * PW) {
+            const int i = t128 / PW, o = t128 % PW;
+            const double* pb = partb + i * PW;
+            double sum = 0.0;
+            for (int wv = 0; wv < active_wgs * 4; ++wv) sum += pb[(size_t)wv * TP_TI * PW + o];
+            a.gpart[(((size_t)rgid * S + (item % S)) * TP_TI + i) * PW + o] = sum;
+          }
+          __threadfence();
+          tp_wg_sync(g);
+          if (t128 == 0) {
+            const unsigned int old = atomicAdd(&a.gcount[rgid], 1u);
+            if (old == (unsigned)S - 1) a.gcount[rgid] = 0;          // ready for the next launch
+            __threadfence();
+            misc[8 + g] = (old == (unsigned)S - 1);
+          }
+          tp_wg_sync(g);
+          finish = misc[8 + g] != 0;
+        }
+        if (finish && t128 < TP_TI * (PW - 1)) {
+          const int i = t128 / (PW - 1), o = t128 % (PW - 1);
+          if (i < rows_valid) {
+            const double* pb = partb + i * PW;
+            double s = 0.0, cnt = 0.0;
+            if (S > 1) {
+              for (int pp = 0; pp < S; ++pp) {
+                const double* gp = a.gpart + (((size_t)rgid * S + pp) * TP_TI + i) * PW;
+                s += __ldcg(gp + o);
+                cnt += __ldcg(gp + PW - 1);
+              }
+            } else {
+#pragma unroll
+              for (int wv = 0; wv < TP_CWARPS; ++wv)
+                if (wv < active_wgs * 4) s += pb[(size_t)wv * TP_TI * PW + o];      // idle warpgroups never wrote theirs
+              for (int wv = 0; wv < active_wgs * 4; ++wv) cnt += pb[(size_t)wv * TP_TI * PW + PW - 1];
+            }
+            const size_t node = (size_t)b * N + i0 + i;
+            if (o < 16) {
+              if (upd_feats) {
+                float inv = 1.f;
+                if (a.flags & EGNN_FLAG_POOL_MEAN) inv = a.has_mask ? (cnt > 0.0 ? 1.f / (float)cnt : 0.f) : 1.f / (float)N;   // :325-330
+                a.m_out[node * a.ldn + o] = __float2bfloat16((float)s * inv);
+              }
+            } else if (o - 16 < C) {
+              if (upd_coors) a.coors_out[node * C + (o - 16)] = xi[i * XC + (o - 16)] + (float)s;             // :315
+            }
+          }
+        }
+}
 
 template <bool GEN>
 __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs a) {
@@ -125,8 +196,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
   float* wqs = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);               // [Q][Hp]
   float* As = wqs + (size_t)Q * Hp;                                           // [2][TI][Hp]
   float* epi = As + (size_t)2 * TP_TI * Hp;                                   // constants
-  float* part = epi + TP_EPI_FLOATS;                                          // [2][16 warps][TI][PW]
-  float* xis = part + 2 * TP_CWARPS * TP_TI * PW;                             // [2][TI][XC]
+  // Sums ACROSS tiles are kept in fp64: the per-tile sums are fp32 (fixed shuffle tree), and adding a few hundred
+  // fp32 numbers in fp64 is exact, so the result does not depend on how the tiles were dealt to warps, work items or
+  // ranks (row-sharded == single GPU, bit for bit, whatever jsplit is).
+  double* part = reinterpret_cast<double*>(epi + TP_EPI_FLOATS);              // [2][16 warps][TI][PW]
+  float* xis = reinterpret_cast<float*>(part + 2 * TP_CWARPS * TP_TI * PW);   // [2][TI][XC]
   uint32_t* mki = reinterpret_cast<uint32_t*>(xis + 2 * TP_TI * XC);          // [2][TI]
   uint32_t* misc = mki + 2 * TP_TI;                                           // [0..1] done counters, [2] tmem ptr, [4..7] last flags
   const int Qf = GEN ? 1 + 2 * a.F : 1, Qh = Q - Qf;
@@ -142,13 +216,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rows_per_graph = a.row1 - a.row0;
   const int rg_per_graph = (rows_per_graph + TP_TI - 1) / TP_TI;
-  const int n_items = a.B * rg_per_graph;
+  // Work items: (graph, row group, j part).  With few row groups per SM (row-sharded graphs, small batches) a row
+  // group's j-blocks are dealt round-robin to S = jsplit items so that the static schedule has enough items to balance;
+  // the S partial sums of a row group meet in global memory and the LAST item to arrive (device-scope counter) adds them
+  // in part order -- deterministic -- and writes the outputs.
+  const int n_items = a.B * rg_per_graph * a.jsplit;          // (jsplit >= 1, set by the launcher)
   const int nchunks = (Hp + TP_KC - 1) / TP_KC;
   const int nsl_last = (Hp - (nchunks - 1) * TP_KC) / 16;        // valid K slabs of the last chunk, 1..4
   const int njb = (N + TP_JB - 1) / TP_JB;
   const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
 
   auto item_rows = [&](int item, int& b, int& i0, int& rows_valid) {
+    item /= a.jsplit;                                                // (the j part is item % jsplit)
     b = item / rg_per_graph;
     i0 = a.row0 + (item - b * rg_per_graph) * TP_TI;
     rows_valid = min(TP_TI, a.row1 - i0);
@@ -246,11 +325,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
       const float* Ab = As + (size_t)buf * TP_TI * Hp;
       const float* xi = xis + buf * TP_TI * XC;
       const uint32_t* mk = mki + buf * TP_TI;
-      float* mypart = part + ((size_t)buf * TP_CWARPS + warp) * TP_TI * PW;
-      for (int x = lane; x < TP_TI * PW; x += 32) mypart[x] = 0.f;
+      double* mypart = part + ((size_t)buf * TP_CWARPS + warp) * TP_TI * PW;
+      for (int x = lane; x < TP_TI * PW; x += 32) mypart[x] = 0.0;
       __syncwarp();
 
-      for (int jb = 0; jb < njb; ++jb) {
+      for (int jb = item % a.jsplit; jb < njb; jb += a.jsplit) {
         if (jb * TP_JB + g * 128 >= N) break;           // this warpgroup's tile lies beyond the graph
         // ---- pair mapping: geometry (and the other per-pair scalar channels) of (i, j) for the rows i
         const int j = jb * TP_JB + g * 128 + t128;
@@ -530,7 +609,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
             for (int o = 0; o < PW; ++o) v[o] += __shfl_xor_sync(0xffffffffu, v[o], off);
           if (lane == 0) {
 #pragma unroll
-            for (int o = 0; o < PW; ++o) mypart[i * PW + o] += v[o];
+            for (int o = 0; o < PW; ++o) mypart[i * PW + o] += (double)v[o];
           }
         }
       }
@@ -547,30 +626,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
       }
       tp_wg_sync(g);
       if (misc[4 + g]) {
-        if (t128 < TP_TI * (PW - 1)) {
-          const int i = t128 / (PW - 1), o = t128 % (PW - 1);
-          if (i < rows_valid) {
-            const float* pb = part + (size_t)buf * TP_CWARPS * TP_TI * PW + i * PW;
-            float s = 0.f;
-#pragma unroll
-            for (int wv = 0; wv < TP_CWARPS; ++wv)
-              if (wv < active_wgs * 4) s += pb[(size_t)wv * TP_TI * PW + o];      // idle warpgroups never wrote theirs
-            const size_t node = (size_t)b * N + i0 + i;
-            if (o < 16) {
-              if (upd_feats) {
-                float inv = 1.f;
-                if (a.flags & EGNN_FLAG_POOL_MEAN) {
-                  float cnt = 0.f;
-                  for (int wv = 0; wv < active_wgs * 4; ++wv) cnt += pb[(size_t)wv * TP_TI * PW + PW - 1];
-                  inv = a.has_mask ? (cnt > 0.f ? 1.f / cnt : 0.f) : 1.f / (float)N;                        // :325-330
-                }
-                a.m_out[node * a.ldn + o] = __float2bfloat16(s * inv);
-              }
-            } else if (o - 16 < C) {
-              if (upd_coors) a.coors_out[node * C + (o - 16)] = xi[i * XC + (o - 16)] + s;                    // :315
-            }
-          }
-        }
+        TpFinishArgs fa;
+        fa.jsplit = a.jsplit; fa.N = N; fa.C = C; fa.ldn = a.ldn; fa.has_mask = a.has_mask; fa.flags = a.flags;
+        fa.gpart = a.gpart; fa.gcount = a.gcount; fa.m_out = a.m_out; fa.coors_out = a.coors_out;
+        tp_finish_item<GEN>(fa, part + (size_t)buf * TP_CWARPS * TP_TI * PW, misc, xi, item, b, i0, rows_valid, active_wgs, g, t128);
         tp_wg_sync(g);                                     // every reader of ring slot `buf` is done
         const int nxt = item + 2 * gridDim.x;
         if (nxt < n_items) stage_item(nxt, buf, t128, [&]() { tp_wg_sync(g); });

@@ -129,13 +129,24 @@ class _EGNNLayerFunction(torch.autograd.Function):
     def forward(ctx, run, feats, coors, edges, label_emb, *params):
         f_out, x_out, saved = run()
         ctx.saved = saved
-        ctx.meta = [(t.dtype, t.device) if t is not None else None for t in (feats, coors, edges, label_emb) + params]
+        tensors = (feats, coors, edges, label_emb) + params
+        ctx.meta = [(t.dtype, t.device) if t is not None else None for t in tensors]
+        # the saved state aliases the inputs and (same device / dtype) the live parameters: remember their versions so
+        # that an in-place edit between forward and backward is reported instead of silently differentiated
+        ctx.versions = [(t, t._version) for t in tensors if t is not None]
         return f_out, x_out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_f, g_x):
         sv = ctx.saved
+        if sv is None:
+            raise RuntimeError("egnn_pytorch_b200: backward through this EGNN layer a second time: the saved forward workspace "
+                               "is released after the first backward (retain_graph=True is not supported; run the forward again)")
+        for t, v in ctx.versions:
+            if t._version != v:
+                raise RuntimeError("egnn_pytorch_b200: a tensor needed for the gradient of an EGNN layer (an input or a parameter) "
+                                   "was modified in place between forward and backward")
         lib, dev, kdt, cdt = nat.load(), sv["dev"], sv["kdt"], sv["cdt"]
         T = sv["tensors"]
         with torch.cuda.device(dev):
@@ -430,6 +441,9 @@ class EGNN(nn.Module):
                              feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr(),
                              nbr_idx=None if nbr is None else nbr.data_ptr(),
                              pre2_out=None if pre2 is None else pre2.data_ptr())
+            if train:     # preflight: configurations the backward kernels cannot run fail HERE, before the forward launches
+                nbb = C.c_size_t()
+                nat.check("egnn_layer_backward_workspace_bytes", lib.egnn_layer_backward_workspace_bytes(C.byref(desc), C.byref(nbb)))
             # training keeps the workspace (per-node tables, pooled messages, neighbour lists) for backward
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if train else _workspace(dev, ws_bytes)
             nat.check("egnn_layer_forward",
@@ -610,13 +624,27 @@ class EGNN_Network(nn.Module):
         def staged(emb):
             return emb.weight if emb.weight.device == dev else emb.weight.to(dev)
 
-        if exists(self.token_emb):
-            feats = F.embedding(feats, staged(self.token_emb))                       # reference :401-402
         if exists(self.pos_emb):
             n = feats.shape[1]
             assert n <= self.num_positions, \
                 f"given sequence length {n} must be less than the number of positions {self.num_positions} set at init"
-            feats = feats + staged(self.pos_emb)[:n].unsqueeze(0)                    # :404-408
+        emb_grad = torch.is_grad_enabled() and any(e is not None and e.weight.requires_grad for e in (self.token_emb, self.pos_emb))
+        if exists(self.token_emb) and not emb_grad and self.token_emb.weight.dtype in _KERNEL_DTYPE:
+            # token + positional embedding in ONE launch (egnn_embed_nodes) instead of embedding, arange, embedding, add
+            tw = staged(self.token_emb)
+            pw = staged(self.pos_emb) if exists(self.pos_emb) else None
+            tok = feats.to(torch.int64).contiguous()
+            n = tok.shape[1]
+            feats = torch.empty((b, n, tw.shape[1]), dtype=tw.dtype, device=dev)
+            with torch.cuda.device(dev):
+                nat.check("egnn_embed_nodes", lib.egnn_embed_nodes(
+                    _KERNEL_DTYPE[tw.dtype], b, n, tw.shape[1], tw.shape[0], _ptr(tok), _ptr(tw), _ptr(pw), _ptr(feats),
+                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        else:                                        # training through the embedding tables: PyTorch autograd
+            if exists(self.token_emb):
+                feats = F.embedding(feats, staged(self.token_emb))                   # reference :401-402
+            if exists(self.pos_emb):
+                feats = feats + staged(self.pos_emb)[:feats.shape[1]].unsqueeze(0)   # :404-408
         if exists(edges) and exists(self.edge_emb):
             edges = F.embedding(edges, staged(self.edge_emb))                        # :410-411
 

@@ -61,6 +61,11 @@ def _all_gather_var(x: torch.Tensor, sizes, group=None):
 def batch_sharded_call(fn, tensors: dict, batch: int, gather: bool = True, group=None):
     """Run `fn(**shard)` on this rank's graphs; optionally all-gather the (feats, coors) outputs."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if gather and batch < world:
+        # checked identically on every rank BEFORE any collective: a rank with an empty shard would have nothing to
+        # contribute to the all-gather and the others would wait for it forever
+        raise ValueError(f"batch_sharded_call(gather=True) needs at least one graph per rank (batch={batch}, world={world}); "
+                         f"use a smaller process group or gather=False")
     shard, (b0, b1) = batch_shard(tensors, rank, world, batch)
     outs = fn(**shard) if b1 > b0 else None
     if not gather:

@@ -210,6 +210,11 @@ int egnn_adj_expand(int32_t B, int32_t N, int32_t num_degrees, const uint8_t* ad
                     int32_t adj_batched, uint8_t* adj_out, uint8_t* labels_out,
                     int32_t* max_row_sum, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Node embedding of EGNN_Network (egnn_pytorch.py:401-408) in one launch: out[b,n,:] = token_emb[tokens[b,n],:] +
+ * pos_emb[n,:] (pos_emb may be NULL).  Tables and output have element type `dtype`; tokens are int64 [B,N]. */
+int egnn_embed_nodes(int32_t dtype, int32_t B, int32_t N, int32_t dim, int32_t num_tokens, const int64_t* tokens,
+                     const void* token_emb, const void* pos_emb, void* out, void* stream);
+
 /* The tcgen05 GEMM the bf16 path uses for its per-node contractions, exposed for unit tests:
  * out[M,N] = act(scale * (A[M,K] W[N,K]^T + bias[N])), A/W bf16 row-major, K and N multiples of 8,
  * act 0 = none / 1 = SiLU, out fp32 (out_f32 = 1) or bf16. */

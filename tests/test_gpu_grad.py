@@ -225,3 +225,24 @@ def test_edge_list_mode_with_empty_slots_matches_directional_derivative():
     assert np.isfinite(an) and abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (fd, an)
     for p in mod.parameters():
         assert torch.isfinite(p.grad).all()
+
+
+def test_second_backward_and_inplace_edits_are_reported():
+    """the saved state aliases inputs / parameters -- a second backward or an in-place edit between forward and
+    backward must raise, not silently differentiate stale data."""
+    from egnn_pytorch_b200 import EGNN
+    torch.manual_seed(0)
+    mod = EGNN(dim=16).cuda()
+    f = torch.randn(1, 12, 16, device="cuda", requires_grad=True)
+    x = torch.randn(1, 12, 3, device="cuda", requires_grad=True)
+    with torch.enable_grad():
+        fo, xo = mod(f, x)
+        loss = fo.sum() + xo.sum()
+        loss.backward(retain_graph=True)
+        with pytest.raises(RuntimeError, match="second time"):
+            loss.backward()
+        fo, xo = mod(f, x)
+        with torch.no_grad():
+            mod.edge_mlp[0].weight.mul_(1.5)            # e.g. an optimizer step before backward
+        with pytest.raises(RuntimeError, match="modified in place"):
+            (fo.sum() + xo.sum()).backward()

@@ -38,6 +38,16 @@ def _worker(rank, world, port, q):
         f, x = parallel.batch_sharded_call(lambda **kw: fn(**kw), ins, batch=3, gather=True)
         want = cases.run_oracle(case)
         assert np.abs(f.numpy() - want[0]).max() < 1e-12 and np.abs(x.numpy() - want[1]).max() < 1e-12
+        # fewer graphs than ranks: every rank raises the same error BEFORE any collective (no hang on the empty shard)
+        one = {k: (v[:1] if torch.is_tensor(v) and v.shape[0] == 3 else v) for k, v in ins.items()}
+        try:
+            parallel.batch_sharded_call(lambda **kw: fn(**kw), one, batch=1, gather=True)
+            raise AssertionError("expected ValueError for batch < world")
+        except ValueError:
+            pass
+        # ... and without the gather the rank with the empty shard simply has nothing to do
+        outs = parallel.batch_sharded_call(lambda **kw: fn(**kw), one, batch=1, gather=False)
+        assert (outs is None) == (rank == 1)
         # --- row sharding of one graph: a single all-gather of [coors | feats], rows stay local
         case = cases.build_case(cases.SPECS["knn_norm_coors"])          # B = 1, N = 40
         ins = {k: torch.from_numpy(np.asarray(v)) for k, v in case["inputs"].items()}
