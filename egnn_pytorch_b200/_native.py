@@ -35,7 +35,7 @@ class LayerDesc(C.Structure):
         ("C", C.c_int32), ("dim", C.c_int32), ("edge_dim", C.c_int32), ("label_dim", C.c_int32),
         ("num_labels", C.c_int32), ("m_dim", C.c_int32), ("fourier", C.c_int32), ("k", C.c_int32),
         ("flags", C.c_uint32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("reserved", C.c_int32),
-        ("valid_radius", C.c_double), ("clamp", C.c_double),
+        ("valid_radius", C.c_double), ("clamp", C.c_double), ("dropout_p", C.c_double), ("dropout_seed", C.c_uint64),
     ]
 
 

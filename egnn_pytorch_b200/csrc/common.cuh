@@ -58,6 +58,32 @@ inline Dims make_dims(const EgnnLayerDesc& d) {
   return s;
 }
 
+// ------------------------------------------------------------------ dropout (training mode, egnn_pytorch.py:176-208)
+// nn.Dropout(p) sits between Linear-1 and SiLU of edge_mlp / node_mlp / coors_mlp.  The masks are never stored: every
+// kernel (forward, recompute, backward) regenerates the keep/drop decision of an element from a counter hash of
+// (seed, stream, element index) -- stream 0: edge hidden (pair, channel), 1: coors hidden (pair, unit), 2: node hidden
+// (node, channel).  Statistically equivalent to the reference's Philox masks, not bit-equal (nothing could be).
+struct DropCfg {
+  unsigned int thr;            // drop when hash < thr;  0 = dropout off
+  float inv_keep;              // 1 / (1 - p)
+  unsigned long long seed;
+};
+__host__ __device__ inline DropCfg make_drop(double p, unsigned long long seed) {
+  DropCfg d;
+  d.thr = p > 0.0 ? (unsigned int)(p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : p * 4294967296.0) : 0u;
+  d.inv_keep = p > 0.0 && p < 1.0 ? (float)(1.0 / (1.0 - p)) : 1.f;
+  d.seed = seed;
+  return d;
+}
+// multiplier of the pre-activation: 0 (dropped) or 1/(1-p) (kept)
+__device__ __forceinline__ float drop_mul(const DropCfg& d, unsigned int stream, unsigned long long idx) {
+  unsigned long long z = idx * 0x9E3779B97F4A7C15ull + d.seed + (unsigned long long)stream * 0xD1B54A32D192ED03ull;
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned int)(z >> 32) < d.thr ? 0.f : d.inv_keep;
+}
+
 // ------------------------------------------------------------------ scalar math
 template <typename T> __device__ __forceinline__ T silu_acc(T x);
 template <> __device__ __forceinline__ float silu_acc<float>(float x) {

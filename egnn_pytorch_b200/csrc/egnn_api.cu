@@ -107,6 +107,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   a.coors_out = uc ? static_cast<T*>(io.coors_out) : nullptr;
   a.hpart = reinterpret_cast<T*>(base + wl.hpart); a.hsplit = wl.hsplit; a.phase = 0;
   a.pre2_out = static_cast<T*>(io.pre2_out);
+  a.drop = make_drop(d.dropout_p, d.dropout_seed);
   {
     StageTimer tm(st, STAGE_PAIR);
     if (s.k > 0) {
@@ -140,7 +141,7 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
     count_launch();
     EGNN_TRY((launch_gemm<T, 1, false>(node_in, s.dim + s.m, static_cast<const T*>(w.node_w1), s.dim + s.m,
                                        static_cast<const T*>(w.node_b1), nullptr, 0, h1, 2 * s.dim, Mr, 2 * s.dim,
-                                       2 * s.dim, s.dim + s.m, map, st)));
+                                       2 * s.dim, s.dim + s.m, map, st, make_drop(d.dropout_p, d.dropout_seed))));
     EGNN_TRY((launch_gemm<T, 0, true>(h1, 2 * s.dim, static_cast<const T*>(w.node_w2), 2 * s.dim,
                                       static_cast<const T*>(w.node_b2), feats, s.dim, static_cast<T*>(io.feats_out),
                                       s.dim, Mr, s.dim, s.dim, 2 * s.dim, map, st)));

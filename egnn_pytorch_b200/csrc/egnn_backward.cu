@@ -75,6 +75,7 @@ static int launch_tiled_recompute(const BwdArgs<T>& a, T* pre2, cudaStream_t st)
   f.m_out = nullptr; f.ld_m = 0; f.coors_out = nullptr;
   f.hpart = pre2; f.hsplit = 1; f.phase = 1;
   f.pre2_out = nullptr;
+  f.drop = a.drop;                                    // the recompute must draw the forward's masks
   const size_t smem = pair_tiled_smem_bytes<T>(a.s, a.L, PP);
   EGNN_TRY(opt_in_smem(pair_dense_tiled_kernel<T, MP, PP>, smem));
   dim3 grid(ceil_div(a.s.N, 4 * PP), a.s.B, 1);
@@ -208,7 +209,8 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
     EGNN_TRY(launch_gemm_acc<T>(go, 1, dim, h1, d2, 1, static_cast<T*>(gr.w.node_w2), d2, dim, d2, M, st));
     EGNN_TRY(launch_colsum<T>(go, dim, M, dim, static_cast<T*>(gr.w.node_b2), st));
     EGNN_TRY(launch_gemm_acc<T>(go, dim, 1, Wn2, d2, 1, ga, d2, M, d2, dim, st));
-    dsilu_mul_kernel<T><<<(int)std::min<size_t>(2048, ((size_t)M * d2 + 255) / 256), 256, 0, st>>>(ga, h1pre, (size_t)M * d2);
+    dsilu_mul_kernel<T><<<(int)std::min<size_t>(2048, ((size_t)M * d2 + 255) / 256), 256, 0, st>>>(ga, h1pre, (size_t)M * d2,
+                                                                                                     make_drop(d.dropout_p, d.dropout_seed));
     EGNN_LAUNCH_CHECK();
     // dWn1[k][c] = sum_r gh1[r][k] node_in[r][c];  db1 = colsum(gh1);  g_node_in = gh1 Wn1
     EGNN_TRY(launch_gemm_acc<T>(ga, 1, d2, node_in, dn, 1, static_cast<T*>(gr.w.node_w1), dn, d2, dn, M, st));
@@ -236,6 +238,7 @@ static int simt_backward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, cons
   a.packed = static_cast<const T*>(packed);
   a.g_node_in = uf ? g_node_in : nullptr; a.ld_g = dn;
   a.g_coors_out = static_cast<const T*>(gr.g_coors_out);
+  a.drop = make_drop(d.dropout_p, d.dropout_seed);
   const bool saved = io.pre2_out != nullptr;                 // the forward kept W2 silu(pre1) per pair
   a.pre2 = saved ? static_cast<const T*>(io.pre2_out)
                  : (s.k == 0 ? reinterpret_cast<const T*>(base + bl.pre2) : nullptr);

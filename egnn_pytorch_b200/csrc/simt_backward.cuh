@@ -66,6 +66,7 @@ struct BwdArgs {
   T* gP;                          // [M][2*Hp]: dL/dA | dL/dB (zeroed by the caller)
   T* g_coors;                     // [B,N,C], pre-loaded with g_coors_out
   T* g_edges;                     // [B,N,N,edge_dim] | null
+  DropCfg drop;                   // the forward's dropout configuration (masks are regenerated, never stored)
 };
 
 template <typename T> __device__ __forceinline__ T dsilu_from(T x, T sg) { return sg * (T(1) + x * (T(1) - sg)); }
@@ -313,6 +314,11 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) pre[u] += tv.v[u];
         }
+        if (a.drop.thr) {                                // edge_mlp Dropout, same mask as the forward
+          const unsigned long long pkey = (((unsigned long long)b * s.N + i) * s.N + j) * s.Hp + c0 + cc;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pre[u] *= (T)drop_mul(a.drop, 0u, pkey + u);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const T hv = silu_acc<T>(pre[u]);             // egnn_pytorch.py:181
@@ -368,8 +374,12 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
 #pragma unroll
           for (int z = 0; z < 4; ++z) t = fma_t(wv.v[z], mm[o + z], t);
         }
+        if (a.drop.thr) {                                // coors_mlp Dropout: a dropped unit is stored as NaN (silu(0) = 0
+          const T f = (T)drop_mul(a.drop, 1u, (((unsigned long long)b * s.N + i) * s.N + j) * U + u);   // adds nothing)
+          t = f == T(0) ? T(NAN) : t * f;
+        }
         tt[tid * UP + u] = t;
-        w0 = fma_t(w4s[u], silu_acc<T>(t), w0);
+        if (t == t) w0 = fma_t(w4s[u], silu_acc<T>(t), w0);
       }
       const T w1 = pm ? w0 : T(0);
       bool inside = true;
@@ -403,8 +413,9 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
       acc_b4 += gw0;
       for (int u = 0; u < U; ++u) {
         const T t = tt[tid * UP + u];
+        if (t != t) continue;                            // dropped unit: no gradient
         const T sg = sigmoid_acc<T>(t);
-        const T gt = gw0 * w4s[u] * dsilu_from<T>(t, sg);
+        const T gt = gw0 * w4s[u] * dsilu_from<T>(t, sg) * (a.drop.thr ? (T)a.drop.inv_keep : T(1));
         const T* w3 = w3s + u * MP;
 #pragma unroll
         for (int o = 0; o < MP; o += 4) {
@@ -468,8 +479,9 @@ pair_bwd1_kernel(const BwdArgs<T> a) {
         const T g0 = gw0s[p];
         if (g0 == T(0)) continue;
         const T t = tt[p * UP + role_u];
+        if (t != t) continue;                            // dropped unit
         const T sg = sigmoid_acc<T>(t);
-        const T gt = g0 * w4u * dsilu_from<T>(t, sg);
+        const T gt = g0 * w4u * dsilu_from<T>(t, sg) * (a.drop.thr ? (T)a.drop.inv_keep : T(1));
         accb3 += gt;
         accw4 = fma_t(g0, t * sg, accw4);
         const T* mrow = mms + p * MP;
@@ -652,6 +664,11 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           }
           if (NL) { lab = lb[cur * BW2_PB + p]; pre += tabs[lab * BW2_TH + tid]; }
         }
+        T fdrop = T(1);
+        if (a.drop.thr) {                                // edge_mlp Dropout: same mask as the forward
+          fdrop = (T)drop_mul(a.drop, 0u, (((unsigned long long)b * N + i0 + row) * N + j) * s.Hp + hh);
+          pre *= fdrop;
+        }
         const T sg = sigmoid_bw(pre);
         const T a1 = pre * sg;
         Pk2<T> ga1p = Pk2<T>::make(T(0), T(0));
@@ -667,7 +684,7 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           gW2p[o / 2 + 1].fma(a1p, g23);
         }
         const T ga1 = ga1p.lo() + ga1p.hi();
-        gp = ga1 * dsilu_from<T>(pre, sg);
+        gp = ga1 * dsilu_from<T>(pre, sg) * fdrop;
         gA += gp;
         if (hv) atomic_add_t<T>(a.gP + ((size_t)b * N + j) * a.ldP + s.Hp + hh, gp);
         if (SIMPLE) {
@@ -855,6 +872,11 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
         }
         if (NL) { lab = labs[cur * BW2_ROWS + p]; pre += tabs[lab * BW2_TH + tid]; }
       }
+      T fdrop = T(1);
+      if (a.drop.thr) {                                  // edge_mlp Dropout: same mask as the forward
+        fdrop = (T)drop_mul(a.drop, 0u, (((unsigned long long)b * N + i0 + p) * N + j) * s.Hp + hh);
+        pre *= fdrop;
+      }
       const T sg = sigmoid_bw(pre);
       const T a1 = pre * sg;
       Pk2<T> ga1p = Pk2<T>::make(T(0), T(0));
@@ -870,7 +892,7 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
         gW2p[o / 2 + 1].fma(a1p, g23);
       }
       const T ga1 = ga1p.lo() + ga1p.hi();
-      const T gp = ga1 * dsilu_from<T>(pre, sg);
+      const T gp = ga1 * dsilu_from<T>(pre, sg) * fdrop;
       gA[p] += gp;
       gB += gp;
       gps[p * BW2_TH + tid] = SIMPLE ? wq0 * gp : gp;      // SIMPLE: the tile holds Wq[h] * g_pre1 already
@@ -1096,12 +1118,14 @@ __global__ void colsum_acc_kernel(const T* __restrict__ X, long ld, int rows, in
   }
 }
 
-// g[x] = g[x] * silu'(pre[x])
+// g[x] = g[x] * silu'(drop(pre[x])) * drop'   (node_mlp: Linear -> Dropout -> SiLU, egnn_pytorch.py:197-199; x = row * cols + col
+// is the element index the forward GEMM epilogue hashed)
 template <typename T>
-__global__ void dsilu_mul_kernel(T* __restrict__ g, const T* __restrict__ pre, size_t n) {
+__global__ void dsilu_mul_kernel(T* __restrict__ g, const T* __restrict__ pre, size_t n, DropCfg drop) {
   for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-    const T p = pre[x];
-    g[x] *= dsilu_from<T>(p, sigmoid_acc<T>(p));
+    T p = pre[x], f = T(1);
+    if (drop.thr) { f = (T)drop_mul(drop, 2u, (unsigned long long)x); p *= f; }
+    g[x] *= dsilu_from<T>(p, sigmoid_acc<T>(p)) * f;
   }
 }
 

@@ -25,6 +25,8 @@ static int validate_desc(const EgnnLayerDesc* d) {
   if (d->label_dim > 0 && (d->num_labels <= 0 || d->num_labels > 255)) return EGNN_ERR_SHAPE;
   if (!(d->flags & (EGNN_FLAG_UPDATE_FEATS | EGNN_FLAG_UPDATE_COORS))) return EGNN_ERR_SHAPE;   // :171
   if (d->reserved != 0) return EGNN_ERR_SHAPE;
+  if (!(d->dropout_p >= 0.0 && d->dropout_p < 1.0)) return EGNN_ERR_SHAPE;
+  if (d->dropout_p > 0.0 && d->dtype == EGNN_DTYPE_BF16) return EGNN_ERR_UNSUPPORTED;     // training runs the fp32 / fp64 kernels
   if (d->row_begin < 0 || d->row_end < 0 || d->row_end > d->N || d->row_begin > d->row_end) return EGNN_ERR_SHAPE;
   return EGNN_OK;
 }
@@ -73,7 +75,7 @@ static int ensure_dynamic_smem(K kernel, size_t smem) {
 
 template <typename T, int ACT, bool RES>
 static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, const T* R, int ldr, T* C,
-                       int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st) {
+                       int ldo, int Mr, int Nv, int Nout, int K, RowMap map, cudaStream_t st, DropCfg drop = DropCfg{0u, 1.f, 0ull}) {
   constexpr int V = 16 / (int)sizeof(T);
   const size_t skinny_smem = (size_t)16 * ((K + V - 1) / V * V) * sizeof(T);
   if (Mr <= 16 && skinny_smem <= 96 * 1024) {
@@ -82,20 +84,20 @@ static int launch_gemm(const T* A, int lda, const T* W, int ldw, const T* bias, 
     const int grid = ceil_div(Nout, SKINNY_WARPS * cols);
     if (cols == 4) {
       EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 4>, skinny_smem));
-      gemm_skinny_kernel<T, ACT, RES, 4><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+      gemm_skinny_kernel<T, ACT, RES, 4><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map, drop);
     } else if (cols == 2) {
       EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 2>, skinny_smem));
-      gemm_skinny_kernel<T, ACT, RES, 2><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+      gemm_skinny_kernel<T, ACT, RES, 2><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map, drop);
     } else {
       EGNN_TRY(ensure_dynamic_smem(gemm_skinny_kernel<T, ACT, RES, 1>, skinny_smem));
-      gemm_skinny_kernel<T, ACT, RES, 1><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+      gemm_skinny_kernel<T, ACT, RES, 1><<<grid, SKINNY_WARPS * 32, skinny_smem, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map, drop);
     }
     EGNN_LAUNCH_CHECK();
     count_launch();
     return EGNN_OK;
   }
   dim3 grid(ceil_div(Nout, 64), ceil_div(Mr, 64));
-  gemm_nt_kernel<T, ACT, RES><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map);
+  gemm_nt_kernel<T, ACT, RES><<<grid, 256, 0, st>>>(A, lda, W, ldw, bias, R, ldr, C, ldo, Mr, Nv, Nout, K, map, drop);
   EGNN_LAUNCH_CHECK();
   count_launch();
   return EGNN_OK;

@@ -85,7 +85,7 @@ template <typename T, int ACT /*0 none, 1 silu, 2 gelu (exact, erf)*/, bool RES>
 __global__ void __launch_bounds__(256)
 gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
                const T* __restrict__ bias, const T* __restrict__ R, int ldr,
-               T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map) {
+               T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map, DropCfg drop) {
   __shared__ T As[16][64 + 4];
   __shared__ T Ws[16][64 + 4];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -132,6 +132,7 @@ gemm_nt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ld
       T v = T(0);
       if (col < Nv) {
         v = acc[i][j] + (bias ? bias[col] : T(0));
+        if (ACT == 1 && drop.thr) v *= (T)drop_mul(drop, 2u, (unsigned long long)row * Nout + col);     // node_mlp Dropout, :198
         if (ACT == 1) v = silu_acc<T>(v);
         if (ACT == 2) v = gelu_acc<T>(v);
         if (RES) v += R[row * ldr + col];
@@ -159,7 +160,7 @@ template <typename T, int ACT, bool RES, int COLS>
 __global__ void __launch_bounds__(SKINNY_WARPS * 32)
 gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw,
                    const T* __restrict__ bias, const T* __restrict__ R, int ldr,
-                   T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map) {
+                   T* __restrict__ Cout, int ldo, int Mr, int Nv, int Nout, int K, RowMap map, DropCfg drop) {
   extern __shared__ __align__(16) unsigned char skinny_smem[];
   T* As = reinterpret_cast<T*>(skinny_smem);                     // [16][Kp], Kp = K rounded up to the vector width
   constexpr int V = SkinnyVec<T>::N;
@@ -230,6 +231,7 @@ gemm_skinny_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
       const size_t row = map(m);
       if (col < Nv) {
         v += bias ? bias[col] : T(0);
+        if (ACT == 1 && drop.thr) v *= (T)drop_mul(drop, 2u, (unsigned long long)row * Nout + col);
         if (ACT == 1) v = silu_acc<T>(v);
         if (ACT == 2) v = gelu_acc<T>(v);
         if (RES) v += R[row * ldr + col];
@@ -299,6 +301,7 @@ struct PairArgs {
   // store partial m_pre sums to hpart [hsplit][B][N][N][MP]; phase 2 adds them up in a fixed order and finishes.
   T* hpart; int hsplit; int phase;      // phase 0 = single pass
   T* pre2_out;                          // optional: [B,N,J][MP] W2 silu(pre1) per pair (J = N dense, k lists), kept for backward
+  DropCfg drop;                         // training-mode dropout of edge_mlp / coors_mlp hidden pre-activations (thr 0 = off)
 };
 
 template <typename T>
@@ -457,6 +460,11 @@ pair_kernel(const PairArgs<T> a) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) pre[u] += tv.v[u];
         }
+        if (a.drop.thr) {                                // edge_mlp Dropout, egnn_pytorch.py:180
+          const unsigned long long pkey = (((unsigned long long)b * s.N + i) * s.N + j) * s.Hp + c0 + cc;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pre[u] *= (T)drop_mul(a.drop, 0u, pkey + u);
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const T hv = silu_acc<T>(pre[u]);             // egnn_pytorch.py:181
@@ -510,6 +518,7 @@ pair_kernel(const PairArgs<T> a) {
 #pragma unroll
           for (int z = 0; z < 4; ++z) t = fma_t(wv.v[z], mm[o + z], t);
         }
+        if (a.drop.thr) t *= (T)drop_mul(a.drop, 1u, (((unsigned long long)b * s.N + i) * s.N + j) * U + u);    // coors_mlp Dropout, :205
         w = fma_t(w4s[u], silu_acc<T>(t), w);
       }
       if (!pm) w = T(0);                                   // :309 (and padding lanes of the tile)
@@ -720,6 +729,14 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
             }
           }
         }
+        if (a.drop.thr) {                                // edge_mlp Dropout, egnn_pytorch.py:180
+#pragma unroll
+          for (int p = 0; p < PP; ++p) {
+            const unsigned long long pkey = (((unsigned long long)b * s.N + irow[p]) * s.N + j) * s.Hp + c0 + cc;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pre[p][u] *= (T)drop_mul(a.drop, 0u, pkey + u);
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const T* w2 = W2s + (cc + u) * MP;
@@ -808,6 +825,7 @@ pair_dense_tiled_kernel(const PairArgs<T> a) {
 #pragma unroll
             for (int z = 0; z < 4; ++z) t = fma_t(wv.v[z], mm[o + z], t);
           }
+          if (a.drop.thr) t *= (T)drop_mul(a.drop, 1u, (((unsigned long long)b * s.N + irow[p]) * s.N + j) * U + u);   // :205
           w = fma_t(w4s[u], silu_acc<T>(t), w);
         }
         if (!pm) w = T(0);

@@ -285,8 +285,6 @@ class EGNN(nn.Module):
         `neighbors` (additive, keyword-only): int tensor [B, N, k] of neighbour indices, -1 = empty slot.  When
         given, the layer runs on exactly these edges and the O(N^2) distance / top-k pass is skipped -- the
         edge-list mode of SURVEY.md section 8(f) (`edge_index_to_neighbors` converts a PyG-style edge_index)."""
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("dropout in training mode is not implemented (SURVEY.md section 8(f) rank 4)")
         fields = self._state_fields()
         train = torch.is_grad_enabled() and (
             feats.requires_grad or coors.requires_grad or (edges is not None and edges.requires_grad) or
@@ -318,8 +316,12 @@ class EGNN(nn.Module):
         assert d == self.dim, f"feature width {d} != dim {self.dim}"
         c = coors.shape[-1]
         kdt = self._kernel_dtype()
-        if train and kdt == torch.bfloat16:
-            kdt = torch.float32                 # the tensor-core kernels are forward-only
+        # nn.Dropout of the three MLPs (reference :176-208) is active in training mode only, grad or no grad -- like
+        # the reference.  The kernels regenerate the masks from (seed, element index) in forward and backward; the seed
+        # is drawn per call from torch's CPU generator, so torch.manual_seed makes a run reproducible.
+        drop_p = float(self.dropout_p) if (self.training and self.dropout_p > 0) else 0.0
+        if (train or drop_p > 0) and kdt == torch.bfloat16:
+            kdt = torch.float32                 # the tensor-core kernels are forward-only and have no dropout
         label_dim = 0 if _label_emb is None else _label_emb.shape[1]
         cont_edge_dim = self.edge_dim - label_dim
         assert (edges is None) == (cont_edge_dim == 0), "edges must be given iff edge_dim > 0"
@@ -353,7 +355,7 @@ class EGNN(nn.Module):
             kdt = torch.float32
         try:
             return self._run(lib, dev, kdt, feats, coors, edges, mask, adj_u8, _edge_labels, _label_emb,
-                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr, train, param_fields)
+                             b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr, train, param_fields, drop_p)
         except nat.EgnnNativeError as e:
             if e.code != nat.ERR_UNSUPPORTED or kdt != torch.bfloat16:
                 raise
@@ -367,7 +369,7 @@ class EGNN(nn.Module):
                          b, n, c, k, flags, cont_edge_dim, label_dim, _rows, nbr)
 
     def _run(self, lib, dev, kdt, feats, coors, edges, mask, adj_u8, labels, label_emb, b, n, c, k, flags,
-             cont_edge_dim, label_dim, rows, nbr=None, train=False, param_fields=None):
+             cont_edge_dim, label_dim, rows, nbr=None, train=False, param_fields=None, drop_p=0.0):
         cdt = torch.float64 if kdt == torch.float64 else torch.float32
         st = self._staged(dev, kdt)
         T = dict(st["tensors"])
@@ -390,7 +392,8 @@ class EGNN(nn.Module):
                 edge_dim=cont_edge_dim, label_dim=label_dim, num_labels=0 if label_emb is None else label_emb.shape[0],
                 m_dim=self.m_dim, fourier=self.fourier_features, k=k, flags=flags,
                 valid_radius=float(self.valid_radius), clamp=float(self.coor_weights_clamp_value or 0.0),
-                row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0)
+                row_begin=0 if rows is None else rows[0], row_end=0 if rows is None else rows[1], reserved=0,
+                dropout_p=0.0, dropout_seed=0)
             nb = C.c_size_t()
             nat.check("egnn_layer_workspace_bytes", lib.egnn_layer_workspace_bytes(C.byref(desc), C.byref(nb)))
             cc = (desc, nb.value)
@@ -398,6 +401,12 @@ class EGNN(nn.Module):
                 self._call_cache.clear()
             self._call_cache[ckey] = cc
         desc, ws_bytes = cc
+        if drop_p > 0:                               # per-call copy: fresh seed, kept with the saved state for backward
+            d2 = nat.LayerDesc()
+            C.memmove(C.byref(d2), C.byref(desc), C.sizeof(nat.LayerDesc))
+            d2.dropout_p = drop_p
+            d2.dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            desc = d2
         wkey = None if lab_w is None else (label_emb.data_ptr(), label_emb._version)
         w = st["wstruct"].get(wkey)
         if w is None:

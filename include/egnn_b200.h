@@ -82,6 +82,10 @@ typedef struct EgnnLayerDesc {
   int32_t  reserved;      /* must be 0                                                    */
   double   valid_radius;  /* used only when k>0 AND io.mask != NULL (:260, :296); +inf ok */
   double   clamp;         /* coor_weights_clamp_value when EGNN_FLAG_CLAMP                */
+  double   dropout_p;     /* training-mode dropout probability of edge_mlp / node_mlp / coors_mlp (egnn_pytorch.py:176-208);
+                             0 = off (eval mode).  fp32 / fp64 kernels only.                */
+  uint64_t dropout_seed;  /* masks are regenerated from (seed, element index) in forward AND backward: pass the SAME
+                             desc to egnn_layer_backward; draw a fresh seed per training step */
 } EgnnLayerDesc;
 
 /*
