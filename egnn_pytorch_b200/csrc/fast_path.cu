@@ -210,7 +210,7 @@ FastWs fast_ws_layout(const FastDims& f, uint32_t flags) {
   auto take = [&](size_t bytes) { size_t r = o; o += round_up(bytes, 256); return r; };
   const bool uf = flags & EGNN_FLAG_UPDATE_FEATS;
   w.Atab = take((size_t)f.s.M * f.Hp * 4);
-  w.Btab = take((size_t)f.s.M * f.Hp * 2);
+  w.Btab = take(((size_t)f.s.M + 128) * f.Hp * 2);      // +128 rows: the dense kernel reads (and discards) up to a tile past the end
   w.node_in = take(uf ? (size_t)f.s.M * f.Kn * 2 : 0);
   w.h1 = take(uf ? (size_t)f.s.M * 2 * f.s.dim * 2 : 0);
   w.nbr_idx = take((size_t)f.s.M * f.s.k * sizeof(int32_t));

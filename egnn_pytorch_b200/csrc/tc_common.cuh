@@ -194,6 +194,11 @@ __device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_
       : "memory");
 }
 
+// one 8-column group (one K=16 slab of the A operand): 4 registers per thread, same fragment layout as above
+__device__ __forceinline__ void tmem_st_16x256b_x1(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
 // ------------------------------------------------------------------ copies into shared memory
 // Ampere-style 16-byte async copy with zero-fill when src_bytes == 0 (generic proxy write).
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr, uint32_t src_bytes) {

@@ -364,19 +364,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
         }
         __syncwarp();
         // ---- fragment mapping: B' rows of this lane's 4 pairs
-        const uint2* Bp[4];
-#pragma unroll
-        for (int rho = 0; rho < 4; ++rho) {
-          const int jr = jb * TP_JB + g * 128 + wq * 32 + lr + 8 * rho;
-          Bp[rho] = reinterpret_cast<const uint2*>(a.Btab + ((size_t)b * N + min(jr, N - 1)) * Hp + 4 * lq);
-        }
+        // (rows lr + 8 rho of the tile are 8 table rows apart: one base pointer + a stride instead of four pointers.  Rows
+        //  beyond the graph are NOT clamped: they read the next graph's rows or the 128 padding rows of the table, and
+        //  their pairs are discarded by `jv` -- NaN-safe, every use is a select)
+        const uint2* Bp0 = reinterpret_cast<const uint2*>(a.Btab + ((size_t)b * N + jb * TP_JB + g * 128 + wq * 32 + lr) * Hp + 4 * lq);
+        const int Bstride = 8 * Hp / 4;                 // uint2 units between rows lr + 8 rho and lr + 8 (rho + 1)
+#define Bp_(rho) (Bp0 + (rho) * Bstride)
         uint2 Bc[4][4];                                 // [rho][slab] B' of the current chunk (bf16 x4 each)
         {
           const int nsl0 = nchunks == 1 ? nsl_last : 4;
 #pragma unroll
           for (int rho = 0; rho < 4; ++rho)
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = sl < nsl0 ? __ldg(Bp[rho] + sl * 4) : make_uint2(0u, 0u);
+            for (int sl = 0; sl < 4; ++sl) Bc[rho][sl] = sl < nsl0 ? __ldg(Bp_(rho) + sl * 4) : make_uint2(0u, 0u);
         }
 
         int pend_c = 0, pend_i = 0;
@@ -410,12 +410,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
           constexpr int NSLC = decltype(nslc)::value;
           const int nsl = NSLC ? NSLC : nsl_last;                   // valid slabs of this chunk
           const int nsl_next = c + 2 == nchunks ? nsl_last : 4;     // ... and of the next one (prefetch)
-          float4 wdr[4];                                // lean: w_d of this lane's 16 channels of the chunk
-          if (!GEN) {
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl)
-              wdr[sl] = sl < nsl ? *reinterpret_cast<const float4*>(wqs + c * TP_KC + sl * 16 + lq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          // Register budget (same-box A/B, tools/ab_variants.sh; every step keeps 128 registers but leaves the compiler more
+          // of them for values in flight between MUFU issue and use): w_d and A' are read from shared memory at the point of
+          // use instead of being held for the chunk / round (-1.1 %, -0.6 %); one B' base pointer + stride (-0.4 %); the
+          // second half of a round stores every slab to TMEM as soon as it is packed (-0.5 %).  Tried and rejected: d_ij read
+          // at use (+1.0 %), slot wait at the top of the round with per-slab stores in both halves (+0.4 %), MMA issue one
+          // slab into the round instead of half a round (+3.1 %).
           // One round = the 64 hidden channels of chunk c for row i and this warp's 32 pairs.  In the last round
           // of a chunk (`reload`), every B' register is re-filled for chunk c+1 right after its last use, so the
           // L2 latency is covered by the rest of that round without a second register buffer.
@@ -428,12 +428,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
             const float* Ai = Ab + (size_t)i * Hp + c * TP_KC + lq * 4;
             const uint32_t ta = tm_wg + TP_TI * 16 + slot * 32;
             float dr[4];
-            float4 avr[4];
             if (!GEN) {
 #pragma unroll
               for (int rho = 0; rho < 4; ++rho) dr[rho] = swg[i * 128 + wq * 32 + lr + 8 * rho];
-#pragma unroll
-              for (int sl = 0; sl < 4; ++sl) avr[sl] = sl < nsl ? *reinterpret_cast<const float4*>(Ai + sl * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {       // rows (lr, lr+8), then (lr+16, lr+24)
@@ -489,11 +486,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
                   if (GEN) {
                     z01 = z[GEN ? sl : 0][r2][0]; z23 = z[GEN ? sl : 0][r2][1];
                   } else {
-                    const float4 av = avr[sl];
+                    const float4 av = *reinterpret_cast<const float4*>(Ai + sl * 16);
                     const float d = dr[rho];
                     const float2 dd = make_float2(d, d);
-                    z01 = tc::ffma2(make_float2(wdr[sl].x, wdr[sl].y), dd, make_float2(av.x, av.y));   // wd*d + A'
-                    z23 = tc::ffma2(make_float2(wdr[sl].z, wdr[sl].w), dd, make_float2(av.z, av.w));
+                    const float4 wv = *reinterpret_cast<const float4*>(wqs + c * TP_KC + sl * 16 + lq * 4);
+                    z01 = tc::ffma2(make_float2(wv.x, wv.y), dd, make_float2(av.x, av.y));   // wd*d + A'
+                    z23 = tc::ffma2(make_float2(wv.z, wv.w), dd, make_float2(av.z, av.w));
                   }
                   const float2 y01 = make_float2(tc::add_bf16_lo(bb.x, z01.x), tc::add_bf16_hi(bb.x, z01.y));  // + B'
                   const float2 y23 = make_float2(tc::add_bf16_lo(bb.y, z23.x), tc::add_bf16_hi(bb.y, z23.y));
@@ -502,15 +500,18 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_pair_kernel(const TcPairArgs
                   // 16x256b fragment: regs {0,1} of a slab -> row lr (+16), regs {2,3} -> row lr+8 (+24); even k low
                   hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(h01.x, h01.y);
                   hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(h23.x, h23.y);
-                  if (reload && sl < nsl_next) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
+                  if (reload && sl < nsl_next) Bc[rho][sl] = __ldg(Bp_(rho) + (c + 1) * 16 + sl * 4);
                 }
+                // second half: the slot is already ours (waited for in the first half) -- store every slab as soon as
+                // it is packed, so that its four staging registers are free for the next slab's values
+                if (half == 1) tc::tmem_st_16x256b_x1(ta + ((uint32_t)16 << 16) + sl * 8, hp[sl * 4], hp[sl * 4 + 1], hp[sl * 4 + 2], hp[sl * 4 + 3]);
               }
               if (half == 0) {
                 issue_pending();                          // round n-1's MMAs, if this warp has the duty
                 tc::mbar_wait_a(empty_a + 8 * slot, ((n / TP_SLOTS) & 1) ^ 1);
                 tc::tc_fence_after();
               }
-              tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
+              if (half == 0) tc::tmem_st_16x256b_x4(ta, hp);
             }
             tc::tmem_wait_st();
             tc::tc_fence_before();
