@@ -551,7 +551,7 @@ inline size_t bwd2_knn_smem_bytes(const Dims& s, int R) {
   return round_up(n * sizeof(T), 16) + 4 * BW2_PB * sizeof(int) + 16;
 }
 
-template <typename T, int MP, int QR>
+template <typename T, int MP, int QR, bool DROP>
 __global__ void __launch_bounds__(BW2_TH)
 pair_bwd2_knn_kernel(const BwdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -665,7 +665,8 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           if (NL) { lab = lb[cur * BW2_PB + p]; pre += tabs[lab * BW2_TH + tid]; }
         }
         T fdrop = T(1);
-        if (a.drop.thr) {                                // edge_mlp Dropout: same mask as the forward
+        if (DROP) {                                      // edge_mlp Dropout: same mask as the forward (own instantiation: the
+                                                         // key arithmetic costs 50 registers when unrolled over the rows)
           fdrop = (T)drop_mul(a.drop, 0u, (((unsigned long long)b * N + i0 + row) * N + j) * s.Hp + hh);
           pre *= fdrop;
         }
@@ -684,7 +685,8 @@ pair_bwd2_knn_kernel(const BwdArgs<T> a) {
           gW2p[o / 2 + 1].fma(a1p, g23);
         }
         const T ga1 = ga1p.lo() + ga1p.hi();
-        gp = ga1 * dsilu_from<T>(pre, sg) * fdrop;
+        gp = ga1 * dsilu_from<T>(pre, sg);
+        if (DROP) gp *= fdrop;
         gA += gp;
         if (hv) atomic_add_t<T>(a.gP + ((size_t)b * N + j) * a.ldP + s.Hp + hh, gp);
         if (SIMPLE) {
@@ -775,7 +777,7 @@ inline size_t bwd2_dense_smem_bytes(const Dims& s, int R) {
   return round_up(n * sizeof(T), 16) + 2 * BW2_ROWS * sizeof(int) + 16;
 }
 
-template <typename T, int MP, int QR>
+template <typename T, int MP, int QR, bool DROP>
 __global__ void __launch_bounds__(BW2_TH)
 pair_bwd2_dense_kernel(const BwdArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -873,7 +875,7 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
         if (NL) { lab = labs[cur * BW2_ROWS + p]; pre += tabs[lab * BW2_TH + tid]; }
       }
       T fdrop = T(1);
-      if (a.drop.thr) {                                  // edge_mlp Dropout: same mask as the forward
+      if (DROP) {                                        // edge_mlp Dropout: same mask as the forward
         fdrop = (T)drop_mul(a.drop, 0u, (((unsigned long long)b * N + i0 + p) * N + j) * s.Hp + hh);
         pre *= fdrop;
       }
@@ -892,7 +894,8 @@ pair_bwd2_dense_kernel(const BwdArgs<T> a) {
         gW2p[o / 2 + 1].fma(a1p, g23);
       }
       const T ga1 = ga1p.lo() + ga1p.hi();
-      const T gp = ga1 * dsilu_from<T>(pre, sg) * fdrop;
+      T gp = ga1 * dsilu_from<T>(pre, sg);
+      if (DROP) gp *= fdrop;
       gA[p] += gp;
       gB += gp;
       gps[p * BW2_TH + tid] = SIMPLE ? wq0 * gp : gp;      // SIMPLE: the tile holds Wq[h] * g_pre1 already

@@ -1,0 +1,141 @@
+// Does the broadcast shared-memory traffic of a round (A' and w_d, needed by the 8 lanes that share a channel quad in the
+// tcgen05.st 16x256b fragment) cost MUFU throughput?  One 512-thread CTA per SM (4 warps per sub-partition, as
+// tc_pair_kernel runs); a "round" = 64 tanh per thread in the kernel's instruction mix, with the operands fetched as:
+//   L=0  registers (no shared-memory traffic)                        -- the ceiling of the mix
+//   L=1  LDS.128 at the point of use, per (half, slab): 16 per round -- what tc_pair_kernel does
+//   L=2  LDS.128 once per round (8), held across both halves
+//   L=3  w_d from __constant__ (4 distinct addresses per warp), A' LDS.128 at use
+//   L=4  bf16 A' and w_d: LDS.64 at use (16 per round, half the bytes)
+//   L=5  A' only (w_d in registers): 8 LDS.128 per round at use
+//   L=6  LDS.32 x4 instead of each LDS.128 (same bytes, 4x the instructions)
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lds_mix_bench tools/lds_mix_bench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+__constant__ float c_wd[4096];
+
+__device__ __forceinline__ unsigned long long pk(float a, float b) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void upk(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+
+__device__ __forceinline__ void four(float4 av, float4 wv, float d, uint2 bb, uint32_t& acc) {
+  unsigned long long z01, z23;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(z01) : "l"(pk(wv.x, wv.y)), "l"(pk(d, d)), "l"(pk(av.x, av.y)));
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(z23) : "l"(pk(wv.z, wv.w)), "l"(pk(d, d)), "l"(pk(av.z, av.w)));
+  float z[4]; upk(z01, z[0], z[1]); upk(z23, z[2], z[3]);
+  float y[4];
+  asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(y[0]) : "r"(bb.x), "f"(z[0]));
+  asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(y[1]) : "r"(bb.x), "f"(z[1]));
+  asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}" : "=f"(y[2]) : "r"(bb.y), "f"(z[2]));
+  asm volatile("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}" : "=f"(y[3]) : "r"(bb.y), "f"(z[3]));
+  float t[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(t[k]) : "f"(y[k]));
+  unsigned long long h01, h23;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(h01) : "l"(pk(y[0], y[1])), "l"(pk(t[0], t[1])));
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(h23) : "l"(pk(y[2], y[3])), "l"(pk(t[2], t[3])));
+  float h[4]; upk(h01, h[0], h[1]); upk(h23, h[2], h[3]);
+  uint32_t p0, p1;
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p0) : "f"(h[1]), "f"(h[0]));
+  asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(h[3]), "f"(h[2]));
+  acc ^= p0 + p1;
+}
+
+__device__ __forceinline__ float4 bf4(uint2 v) {
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+
+template <int L>
+__global__ void __launch_bounds__(512) kround(float* out, int iters, float seed, int H) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float* Ab = reinterpret_cast<float*>(smraw);           // [4][H]  A' rows of the item
+  float* wq = Ab + 4 * 4096;                             // [H]     w_d
+  for (int e = threadIdx.x; e < 5 * 4096; e += 512) Ab[e] = 1e-3f * (e & 255);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, lq = lane & 3;
+  uint2 Bc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) Bc[r][s] = make_uint2(0x3c003c00u + r + threadIdx.x, 0x3c003c00u + s);
+  float dr[4] = {seed, seed + 1.f, seed + 2.f, seed + 3.f};
+  float4 ra[4], rw[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { ra[s] = make_float4(seed, seed * 2, seed * 3, seed * 4); rw[s] = make_float4(0.01f, 0.02f, 0.03f, 0.04f * seed); }
+  uint32_t acc = 0;
+  const int nchunks = H / 64;
+  for (int it = 0; it < iters; ++it) {
+    const int c = it % nchunks, i = it & 3;
+    const float* Ai = Ab + i * 4096 + c * 64 + lq * 4;
+    const float* wi = wq + c * 64 + lq * 4;
+    float4 ha[4], hw[4];
+    if (L == 2) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) { ha[s] = *reinterpret_cast<const float4*>(Ai + s * 16); hw[s] = *reinterpret_cast<const float4*>(wi + s * 16); }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        float4 av, wv;
+        if (L == 0) { av = ra[s]; wv = rw[s]; }
+        else if (L == 1) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = *reinterpret_cast<const volatile float4*>(wi + s * 16); }
+        else if (L == 2) { av = ha[s]; wv = hw[s]; }
+        else if (L == 3) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = *reinterpret_cast<const float4*>(c_wd + c * 64 + lq * 4 + s * 16); }
+        else if (L == 4) {
+          const uint2 a2 = *reinterpret_cast<const volatile uint2*>(reinterpret_cast<const __nv_bfloat16*>(Ab) + i * 4096 + c * 64 + lq * 4 + s * 16);
+          const uint2 w2 = *reinterpret_cast<const volatile uint2*>(reinterpret_cast<const __nv_bfloat16*>(wq) + c * 64 + lq * 4 + s * 16);
+          av = bf4(a2); wv = bf4(w2);
+        } else if (L == 5) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = rw[s]; }
+        else {
+          const volatile float* pa = Ai + s * 16; const volatile float* pw = wi + s * 16;
+          av = make_float4(pa[0], pa[1], pa[2], pa[3]); wv = make_float4(pw[0], pw[1], pw[2], pw[3]);
+        }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) four(av, wv, dr[half * 2 + r2], Bc[half * 2 + r2][s], acc);
+      }
+    }
+    dr[it & 3] += 1e-3f;
+  }
+  if (acc == 0x12345678u) out[0] = __uint_as_float(acc);
+}
+
+static float* g_out; static int g_sms;
+template <int L> double run(int iters, int warps_per_smsp) {
+  cudaFuncSetAttribute(kround<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  const int ctas = g_sms * (warps_per_smsp / 4);
+  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, 64, 1.0f, 2048);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, iters, 1.0f, 2048);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+template <int L> void report(const char* name) {
+  const int it = 8192;
+  for (int w = 4; w <= 8; w += 4) {
+    const double ms = run<L>(it, w);
+    const double tanh_total = (double)g_sms * (w / 4) * 512 * it * 64;
+    printf("%-58s %dw/SMSP %8.3f ms  %6.2f tanh/clk/SM @1965MHz\n", name, w, ms, tanh_total / (ms * 1e-3) / g_sms / 1.965e9);
+  }
+}
+
+int main() {
+  cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+  g_sms = p.multiProcessorCount;
+  cudaMalloc(&g_out, 4);
+  printf("%s, %d SMs\n", p.name, g_sms);
+  report<0>("L0 operands in registers");
+  report<1>("L1 LDS.128 at use (16 / round)  [tc_pair_kernel]");
+  report<2>("L2 LDS.128 once per round (8), held");
+  report<3>("L3 w_d from __constant__, A' LDS.128 at use");
+  report<4>("L4 bf16 A' and w_d, LDS.64 at use");
+  report<5>("L5 A' only LDS.128 at use (8 / round)");
+  report<6>("L6 LDS.32 x4 per quad");
+  if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
+  return 0;
+}
