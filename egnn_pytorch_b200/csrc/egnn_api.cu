@@ -5,6 +5,7 @@
 #include "fast_path.h"
 #include "profile.h"
 #include "simt_host.cuh"
+#include "small_node.cuh"
 #include <algorithm>
 
 namespace egnn {
@@ -86,10 +87,21 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   // 2. per-node tables  A = h W1[:, :dim]^T + b1,  B = h W1[:, dim:2dim]^T   (split of :287's Linear-1)
   {
     StageTimer tm(st, STAGE_NODE_PRE);
-    EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1, s.E, static_cast<const T*>(w.edge_b1), nullptr, 0, P,
-                                        2 * s.Hp, s.M, s.H, s.Hp, s.dim, ident, st)));
-    EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1 + s.dim, s.E, nullptr, nullptr, 0, P + s.Hp, 2 * s.Hp,
-                                        s.M, s.H, s.Hp, s.dim, ident, st)));
+    if (s.dim <= SN_DIM_MAX && s.M <= SN_TABLES_M_MAX && tables_small_simt_smem<T>(s.dim, s.Hp) <= SMALL_NODE_SMEM_MAX) {   // narrow layer, few nodes: one launch
+      TablesSmallSimtArgs<T> t;
+      t.feats = feats; t.W1 = W1; t.b1 = static_cast<const T*>(w.edge_b1); t.P = P;
+      t.M = s.M; t.dim = s.dim; t.H = s.H; t.Hp = s.Hp; t.E = s.E;
+      const size_t smem = tables_small_simt_smem<T>(s.dim, s.Hp);
+      EGNN_TRY(ensure_dynamic_smem(tables_small_simt_kernel<T>, smem));
+      tables_small_simt_kernel<T><<<std::min(ceil_div(s.M, SN_WARPS), 4 * small_node_sms()), SN_WARPS * 32, smem, st>>>(t);
+      EGNN_LAUNCH_CHECK();
+      count_launch();
+    } else {
+      EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1, s.E, static_cast<const T*>(w.edge_b1), nullptr, 0, P,
+                                          2 * s.Hp, s.M, s.H, s.Hp, s.dim, ident, st)));
+      EGNN_TRY((launch_gemm<T, 0, false>(feats, s.dim, W1 + s.dim, s.E, nullptr, nullptr, 0, P + s.Hp, 2 * s.Hp,
+                                          s.M, s.H, s.Hp, s.dim, ident, st)));
+    }
   }
   // 3. fused edge step
   PairArgs<T> a;
@@ -133,7 +145,22 @@ static int simt_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const
   StageTimer post_tm(st, STAGE_NODE_POST);
   const int Rr = s.row1 - s.row0, Mr = s.B * Rr;
   const RowMap map{Rr, s.N, s.row0};
-  if (uf) {
+  if (uf && d.dropout_p == 0.0 && s.dim <= SN_DIM_MAX && node_small_simt_smem<T>(s.dim, s.m) <= SMALL_NODE_SMEM_MAX) {
+    // narrow layer: LayerNorm, concat, both Linear layers and the residual in one launch (node_in / h1 still written)
+    NodeSmallSimtArgs<T> n;
+    n.feats = feats; n.node_in = node_in; n.h1 = h1;
+    n.wn1 = static_cast<const T*>(w.node_w1); n.bn1 = static_cast<const T*>(w.node_b1);
+    n.wn2 = static_cast<const T*>(w.node_w2); n.bn2 = static_cast<const T*>(w.node_b2);
+    n.lng = static_cast<const T*>(w.norm_g); n.lnb = static_cast<const T*>(w.norm_b);
+    n.out = static_cast<T*>(io.feats_out);
+    n.B = s.B; n.N = s.N; n.dim = s.dim; n.m = s.m; n.row0 = s.row0; n.row1 = s.row1;
+    n.do_norm = (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0;
+    const size_t smem = node_small_simt_smem<T>(s.dim, s.m);
+    EGNN_TRY(ensure_dynamic_smem(node_update_small_simt_kernel<T>, smem));
+    node_update_small_simt_kernel<T><<<std::min(ceil_div(Mr, SN_WARPS), 4 * small_node_sms()), SN_WARPS * 32, smem, st>>>(n);
+    EGNN_LAUNCH_CHECK();
+    count_launch();
+  } else if (uf) {
     ln_concat_kernel<T><<<ceil_div(Mr * 32, 256), 256, 0, st>>>(
         feats, static_cast<const T*>(w.norm_g), static_cast<const T*>(w.norm_b), node_in, s.dim + s.m, s.dim, Mr,
         map, (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0);

@@ -10,6 +10,7 @@
 #include "tc_gemm.cuh"
 #include "tc_pair.cuh"
 #include "tc_knn.cuh"
+#include "small_node.cuh"
 
 namespace egnn {
 
@@ -344,24 +345,38 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
 
   {  // per-node tables, pre-halved for the tanh form of SiLU:  A' = 0.5 (h W1_i^T + b1),  B' = 0.5 h W1_j^T
     StageTimer tm(st, STAGE_NODE_PRE);
-    TcGemmArgs g{};
-    g.lda = s.dim; g.K = s.dim; g.Nv = f.Hp; g.Nout = f.Hp; g.scale = 0.5f; g.act = 0; g.R = nullptr; g.ldr = 0; g.ldo = f.Hp;
-    g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1i); g.ldw = s.dim;
-    g.bias = reinterpret_cast<const float*>(pk + L.b1);
-    g.out_f32 = 1;
-    TcGemmArgs gb = g;                                    // B' = 0.5 h W1_j^T over ALL rows
-    gb.A = feats; gb.M = s.M;
-    gb.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j); gb.bias = nullptr;
-    gb.out = Btab; gb.out_f32 = 0;
-    if (all_rows) {                                       // both tables in one launch (same rows, same activations)
-      g.A = feats; g.M = s.M; g.out = Atab;
-      EGNN_TRY(launch_tc_gemm(g, st, &gb));
+    if (s.dim <= SN_DIM_MAX && s.M <= SN_TABLES_M_MAX) {  // narrow layer, few nodes: one warp per node, one launch (small_node.cuh)
+      TablesSmallArgs t{};
+      t.feats = feats; t.w1i = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1i); t.w1j = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j);
+      t.b1 = reinterpret_cast<const float*>(pk + L.b1); t.Atab = Atab; t.Btab = Btab;
+      t.M = s.M; t.N = s.N; t.dim = s.dim; t.Hp = f.Hp; t.row0 = r0; t.row1 = r1;
+      const size_t smem = tables_small_smem(s.dim, f.Hp);
+      EGNN_TRY((ensure_dyn_smem<6>(tables_small_kernel, smem)));
+      int sms = 0;
+      EGNN_TRY(sm_count(&sms));
+      tables_small_kernel<<<std::min(ceil_div(s.M, SN_WARPS), 4 * sms), SN_WARPS * 32, smem, st>>>(t);
+      EGNN_LAUNCH_CHECK();
+      count_launch();
     } else {
-      for (int sg = 0; sg < nseg; ++sg) {
-        g.A = feats + seg_begin(sg) * s.dim; g.M = seg_rows; g.out = Atab + seg_begin(sg) * f.Hp;
-        EGNN_TRY(launch_tc_gemm(g, st));
+      TcGemmArgs g{};
+      g.lda = s.dim; g.K = s.dim; g.Nv = f.Hp; g.Nout = f.Hp; g.scale = 0.5f; g.act = 0; g.R = nullptr; g.ldr = 0; g.ldo = f.Hp;
+      g.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1i); g.ldw = s.dim;
+      g.bias = reinterpret_cast<const float*>(pk + L.b1);
+      g.out_f32 = 1;
+      TcGemmArgs gb = g;                                    // B' = 0.5 h W1_j^T over ALL rows
+      gb.A = feats; gb.M = s.M;
+      gb.W = reinterpret_cast<const __nv_bfloat16*>(pk + L.w1j); gb.bias = nullptr;
+      gb.out = Btab; gb.out_f32 = 0;
+      if (all_rows) {                                       // both tables in one launch (same rows, same activations)
+        g.A = feats; g.M = s.M; g.out = Atab;
+        EGNN_TRY(launch_tc_gemm(g, st, &gb));
+      } else {
+        for (int sg = 0; sg < nseg; ++sg) {
+          g.A = feats + seg_begin(sg) * s.dim; g.M = seg_rows; g.out = Atab + seg_begin(sg) * f.Hp;
+          EGNN_TRY(launch_tc_gemm(g, st));
+        }
+        EGNN_TRY(launch_tc_gemm(gb, st));
       }
-      EGNN_TRY(launch_tc_gemm(gb, st));
     }
   }
   if (s.k == 0) {  // fused edge kernel, dense all-pairs (persistent: one CTA per SM walks the row groups)
@@ -451,19 +466,23 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
     a.m_out = uf ? node_in + s.dim : nullptr;
     a.coors_out = uc ? static_cast<float*>(io.coors_out) : nullptr;
     const int mode = knn_mode(f);
-    const size_t smem = tc_knn_smem_bytes(f.Hp, mode, f.QT);
-    dim3 grid(ceil_div(R, TK_ROWS), s.B);
+    const int rows = tc_knn_rows_per_cta(f.Hp, mode, f.QT);         // 8 (two CTAs per SM) when shared memory allows
+    const size_t smem = tc_knn_smem_bytes(f.Hp, mode, f.QT, rows);
+    dim3 grid(ceil_div(R, rows), s.B);
     if (R > 0) {
+#define EGNN_TC_KNN_LAUNCH(TAG, MODE_, ROWS_)                                                  \
+  do {                                                                                          \
+    EGNN_TRY((ensure_dyn_smem<TAG>(tc_knn_kernel<MODE_, ROWS_>, smem)));                        \
+    tc_knn_kernel<MODE_, ROWS_><<<grid, ROWS_ * 32, smem, st>>>(a);                             \
+  } while (0)
       if (mode == TK_LEAN) {
-        EGNN_TRY((ensure_dyn_smem<3>(tc_knn_kernel<TK_LEAN>, smem)));
-        tc_knn_kernel<TK_LEAN><<<grid, TK_THREADS, smem, st>>>(a);
+        if (rows == 8) EGNN_TC_KNN_LAUNCH(3, TK_LEAN, 8); else EGNN_TC_KNN_LAUNCH(13, TK_LEAN, 16);
       } else if (mode == TK_EDGES) {
-        EGNN_TRY((ensure_dyn_smem<4>(tc_knn_kernel<TK_EDGES>, smem)));
-        tc_knn_kernel<TK_EDGES><<<grid, TK_THREADS, smem, st>>>(a);
+        if (rows == 8) EGNN_TC_KNN_LAUNCH(4, TK_EDGES, 8); else EGNN_TC_KNN_LAUNCH(14, TK_EDGES, 16);
       } else {
-        EGNN_TRY((ensure_dyn_smem<5>(tc_knn_kernel<TK_GEN>, smem)));
-        tc_knn_kernel<TK_GEN><<<grid, TK_THREADS, smem, st>>>(a);
+        if (rows == 8) EGNN_TC_KNN_LAUNCH(5, TK_GEN, 8); else EGNN_TC_KNN_LAUNCH(15, TK_GEN, 16);
       }
+#undef EGNN_TC_KNN_LAUNCH
       EGNN_LAUNCH_CHECK();
       count_launch();
     }
@@ -471,6 +490,21 @@ int fast_forward(const EgnnLayerDesc& d, const EgnnLayerWeights& w, const void* 
   StageTimer post(st, STAGE_NODE_POST);
   __nv_bfloat16* fout = static_cast<__nv_bfloat16*>(io.feats_out);
   if (uf) {  // h' = node_mlp([LN(h) | m_i]) + h
+    if (s.dim <= SN_DIM_MAX && R > 0) {                   // narrow layer: LayerNorm, concat, both Linear layers and the residual in one launch
+      NodeSmallArgs n{};
+      n.feats = feats; n.node_in = node_in; n.wn1 = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn1);
+      n.bn1 = reinterpret_cast<const float*>(pk + L.bn1); n.wn2 = reinterpret_cast<const __nv_bfloat16*>(pk + L.wn2);
+      n.bn2 = reinterpret_cast<const float*>(pk + L.bn2); n.lng = reinterpret_cast<const float*>(pk + L.lng);
+      n.lnb = reinterpret_cast<const float*>(pk + L.lnb); n.out = fout;
+      n.B = s.B; n.N = s.N; n.dim = s.dim; n.Kn = f.Kn; n.m = s.m; n.row0 = r0; n.row1 = r1; n.do_norm = (d.flags & EGNN_FLAG_NORM_FEATS) ? 1 : 0;
+      const size_t smem = node_small_smem(s.dim, f.Kn);
+      EGNN_TRY((ensure_dyn_smem<7>(node_update_small_kernel, smem)));
+      int sms = 0;
+      EGNN_TRY(sm_count(&sms));
+      node_update_small_kernel<<<std::min(ceil_div(s.B * R, SN_WARPS), 4 * sms), SN_WARPS * 32, smem, st>>>(n);
+      EGNN_LAUNCH_CHECK();
+      count_launch();
+    } else
     for (int sg = 0; sg < nseg; ++sg) {
       const size_t o = seg_begin(sg);
       ln_concat_bf16_kernel<<<ceil_div(seg_rows * 32, 256), 256, 0, st>>>(

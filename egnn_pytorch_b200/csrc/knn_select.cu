@@ -81,15 +81,15 @@ __device__ __forceinline__ void warp_merge(T& bkey, int& bidx, T ckey, int cidx,
   for (int stride = 16; stride > 0; stride >>= 1) cmpex<T>(bkey, bidx, lane, stride, true);
 }
 
-constexpr int SEL_WARPS = 8;        // rows per CTA (one warp each), all of the same graph
+constexpr int SEL_WARPS_MAX = 16;   // rows per CTA (one warp each, all of the same graph): 16, or 8 for grids that would not fill the GPU
 constexpr int SEL_JC = 1024;        // candidates staged per pass: coordinates as SoA + mask bytes in shared memory
 
 template <typename T>
-inline size_t sel_smem_bytes(int C) {
-  return (size_t)C * SEL_JC * sizeof(T) + SEL_JC + (size_t)SEL_WARPS * 64 * (sizeof(T) + sizeof(int)) + 64;
+inline size_t sel_smem_bytes(int C, int warps = SEL_WARPS_MAX) {
+  return (size_t)C * SEL_JC * sizeof(T) + SEL_JC + (size_t)warps * 64 * (sizeof(T) + sizeof(int)) + 64;
 }
 
-template <typename T>
+template <typename T, int SEL_WARPS>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 knn_warp_select_kernel(const SelArgs<T> a) {
   extern __shared__ __align__(16) unsigned char sel_sm[];
@@ -120,53 +120,65 @@ knn_warp_select_kernel(const SelArgs<T> a) {
   for (int jc0 = 0; jc0 < a.N; jc0 += SEL_JC) {
     const int jn = min(SEL_JC, a.N - jc0);
     __syncthreads();                   // previous pass fully consumed
-    for (int e = threadIdx.x; e < jn * a.C; e += SEL_WARPS * 32) {
-      const int jj = e / a.C, c = e - jj * a.C;
-      xs[c * SEL_JC + jj] = a.coors[((size_t)b * a.N + jc0) * a.C + e];
+    for (int jj = threadIdx.x; jj < jn; jj += SEL_WARPS * 32) {          // one candidate per thread: no index division
+      const T* src = a.coors + ((size_t)b * a.N + jc0 + jj) * a.C;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < a.C) xs[c * SEL_JC + jj] = src[c];
+      if (a.mask) ms[jj] = a.mask[(size_t)b * a.N + jc0 + jj];
     }
-    if (a.mask)
-      for (int jj = threadIdx.x; jj < jn; jj += SEL_WARPS * 32) ms[jj] = a.mask[(size_t)b * a.N + jc0 + jj];
     __syncthreads();
 
-    for (int j0 = 0; j0 < jn; j0 += 32) {
-      const int jj = j0 + lane, j = jc0 + jj;
-      const bool jvalid = jj < jn;
-      T key = INF;
-      if (jvalid) {
-        T d = T(0);
+    // two groups of 32 candidates per trip: their distance chains overlap; each group is then filtered against the
+    // current k-th entry and queued (the second group may see a threshold one merge old -- it only queues a few more)
+    for (int j0 = 0; j0 < jn; j0 += 64) {
+      T key[2];
+      bool pass[2];
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          if (c < a.C) d = sq_acc<T>(xi[c] - xs[c * SEL_JC + jj], d);
-        if (a.mask && !(mask_i && ms[jj])) d = T(1e5);
-        if (adjrow) {
-          if (i == j) d = T(-1);
-          else if (adjrow[j]) d = T(0);
+      for (int u = 0; u < 2; ++u) {
+        const int jj = j0 + 32 * u + lane, j = jc0 + jj;
+        const bool jvalid = jj < jn;
+        key[u] = INF;
+        if (jvalid) {
+          T d = T(0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (c < a.C) d = sq_acc<T>(xi[c] - xs[c * SEL_JC + jj], d);
+          if (a.mask && !(mask_i && ms[jj])) d = T(1e5);
+          if (adjrow) {
+            if (i == j) d = T(-1);
+            else if (adjrow[j]) d = T(0);
+          }
+          key[u] = d;
         }
-        key = d;
+        pass[u] = jvalid && lex_less<T>(key[u], j, thr_key, thr_idx);
       }
-      const bool pass = jvalid && lex_less<T>(key, j, thr_key, thr_idx);
-      const unsigned bal = __ballot_sync(0xffffffffu, pass);
-      if (bal == 0) continue;
-      if (pass) {
-        const int pos = count + __popc(bal & ((1u << lane) - 1));
-        myqk[pos] = key;
-        myqi[pos] = j;
-      }
-      count += __popc(bal);
-      __syncwarp();
-      if (count >= 32) {
-        T ckey = myqk[lane];
-        int cidx = myqi[lane];
-        __syncwarp();
-        if (lane + 32 < count) {         // shift the tail of the queue down
-          T tk = myqk[lane + 32]; int ti = myqi[lane + 32];
-          myqk[lane] = tk; myqi[lane] = ti;
+      if (!__any_sync(0xffffffffu, pass[0] || pass[1])) continue;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned bal = __ballot_sync(0xffffffffu, pass[u]);
+        if (bal == 0) continue;
+        if (pass[u]) {
+          const int pos = count + __popc(bal & ((1u << lane) - 1));
+          myqk[pos] = key[u];
+          myqi[pos] = jc0 + j0 + 32 * u + lane;
         }
-        count -= 32;
+        count += __popc(bal);
         __syncwarp();
-        warp_merge<T>(bkey, bidx, ckey, cidx, lane);
-        thr_key = shfl_idx_t<T>(bkey, a.k - 1);
-        thr_idx = __shfl_sync(0xffffffffu, bidx, a.k - 1);
+        if (count >= 32) {
+          T ckey = myqk[lane];
+          int cidx = myqi[lane];
+          __syncwarp();
+          if (lane + 32 < count) {         // shift the tail of the queue down
+            T tk = myqk[lane + 32]; int ti = myqi[lane + 32];
+            myqk[lane] = tk; myqi[lane] = ti;
+          }
+          count -= 32;
+          __syncwarp();
+          warp_merge<T>(bkey, bidx, ckey, cidx, lane);
+          thr_key = shfl_idx_t<T>(bkey, a.k - 1);
+          thr_idx = __shfl_sync(0xffffffffu, bidx, a.k - 1);
+        }
       }
     }
   }
@@ -231,17 +243,24 @@ static int launch_select(int B, int N, int C, int k, const void* coors, const ui
   a.out_idx = out_idx; a.out_ok = out_ok;
   const int rows = B * N;
   if (k <= 32) {
-    const size_t smem = sel_smem_bytes<T>(C);
     static bool attr_set[64] = {false};
     int dev = 0;
     EGNN_CUDA_TRY(cudaGetDevice(&dev));
-    if (smem > 48 * 1024 && dev < 64 && !attr_set[dev]) {
-      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sel_smem_bytes<T>(8)));
+    if (dev < 64 && !attr_set[dev]) {
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sel_smem_bytes<T>(8, 16)));
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sel_smem_bytes<T>(8, 8)));
       attr_set[dev] = true;
     }
-    dim3 grid(ceil_div(N, SEL_WARPS), B);
-    knn_warp_select_kernel<T><<<grid, SEL_WARPS * 32, smem, st>>>(a);
+    // 16 rows per CTA halve the staging work per row; small problems keep 8 so that more SMs take part
+    if ((long)B * ceil_div(N, 16) >= 296) {
+      dim3 grid(ceil_div(N, 16), B);
+      knn_warp_select_kernel<T, 16><<<grid, 16 * 32, sel_smem_bytes<T>(C, 16), st>>>(a);
+    } else {
+      dim3 grid(ceil_div(N, 8), B);
+      knn_warp_select_kernel<T, 8><<<grid, 8 * 32, sel_smem_bytes<T>(C, 8), st>>>(a);
+    }
   } else {
     int Npad = 1;
     while (Npad < N) Npad <<= 1;

@@ -26,10 +26,9 @@
 
 namespace egnn {
 
-constexpr int TK_ROWS = 16;        // query rows per CTA (one per warp)
+constexpr int TK_ROWS = 16;        // query rows per CTA (one per warp): 16, or 8 when two CTAs then fit on an SM
 constexpr int TK_KC = 64;
 constexpr int TK_SLOTS = 3;
-constexpr int TK_THREADS = 512;
 constexpr int TK_WGCOLS = 128;     // 16 accumulator + 3 x 32 operand columns (+16 spare)
 constexpr int TK_QE = 4;           // edge channels folded per pair (edge_dim <= 4, zero padded)
 
@@ -59,19 +58,28 @@ struct TcKnnArgs {
 // channels of the Wq table staged in shared memory: 1 (lean), 1 + TK_QE (edges), Q (generic)
 inline int tc_knn_wq_rows(int mode, int Q) { return mode == TK_LEAN ? 1 : mode == TK_EDGES ? 1 + TK_QE : Q; }
 
-inline size_t tc_knn_smem_bytes(int Hp, int mode, int Q = 1) {
+inline size_t tc_knn_smem_bytes(int Hp, int mode, int Q = 1, int rows = TK_ROWS) {
   size_t n = 0;
   n += (size_t)Hp * 32;                       // W2 slabs
-  n += (size_t)TK_ROWS * Hp * 4;              // A rows (fp32)
+  n += (size_t)rows * Hp * 4;                 // A rows (fp32)
   n += (size_t)tc_knn_wq_rows(mode, Q) * Hp * 4;   // wd | We | generic Wq
   n += (size_t)TP_EPI_FLOATS * 4;             // epilogue constants
-  n += mode == TK_GEN ? (size_t)TK_ROWS * Q * 32 * 4 : 0;   // per-warp scalar tile [Q][32 slots]
+  n += mode == TK_GEN ? (size_t)rows * Q * 32 * 4 : 0;   // per-warp scalar tile [Q][32 slots]
   n += 64 + 32 * 8;                           // tmem pointer, mbarriers
   return n + 128;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a) {
+// Rows per CTA: a CTA runs its prologue (TMEM allocation, staging W2 / A' / channel weights, the dependent gathers of
+// neighbour indices, coordinates and edge channels), 17-odd chunks and the coors-MLP epilogue back to back, so with one
+// CTA per SM the MUFU pipe idles through every prologue and epilogue (c4: 52 us per CTA for 19 us of MUFU work).  With
+// ROWS = 8 (256 threads, 256 TMEM columns, half the A' rows) two CTAs are resident and cover each other's phases; the
+// host takes ROWS = 8 whenever two CTAs fit in shared memory (rows_per_cta below).
+inline int tc_knn_rows_per_cta(int Hp, int mode, int Q) { return 2 * (tc_knn_smem_bytes(Hp, mode, Q, 8) + 1024) <= 227 * 1024 ? 8 : 16; }
+
+template <int MODE, int ROWS>
+__global__ void __launch_bounds__(ROWS * 32, ROWS == 8 ? 2 : 1) tc_knn_kernel(const TcKnnArgs a) {
+  constexpr int TK_THREADS = ROWS * 32;
+  constexpr int TK_TMEM = ROWS / 4 * TK_WGCOLS;                               // 512 | 256 columns
   constexpr bool EDGES = MODE == TK_EDGES, GEN = MODE == TK_GEN;
   constexpr int NX = GEN ? TP_CMAX : 3;                                       // coordinate registers
   constexpr int PW = GEN ? 16 + TP_CMAX + 1 : 20;                             // reduced record: 16 m | coords | count
@@ -80,11 +88,11 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   const int C = GEN ? a.C : 3, Q = GEN ? a.Q : 1;
   unsigned char* w2s = sm;
   float* As = reinterpret_cast<float*>(w2s + (size_t)Hp * 32);                // [16][Hp]
-  float* wds = As + (size_t)TK_ROWS * Hp;                                     // [Hp]  (generic: Wq [Q][Hp])
+  float* wds = As + (size_t)ROWS * Hp;                                     // [Hp]  (generic: Wq [Q][Hp])
   float* wes = wds + Hp;                                                      // [QE][Hp] (EDGES only)
   float* epi = wds + (size_t)(GEN ? Q : EDGES ? 1 + TK_QE : 1) * Hp;
   float* stile = epi + TP_EPI_FLOATS;                                         // [16 warps][Q][32] (GEN only)
-  uint32_t* misc = reinterpret_cast<uint32_t*>(stile + (GEN ? TK_ROWS * Q * 32 : 0));   // [0] tmem pointer
+  uint32_t* misc = reinterpret_cast<uint32_t*>(stile + (GEN ? ROWS * Q * 32 : 0));   // [0] tmem pointer
   uint64_t* bars = reinterpret_cast<uint64_t*>(misc + 16);
   uint64_t* full = bars;                      // [4][SLOTS]
   uint64_t* empty = bars + 4 * TK_SLOTS;      // [4][SLOTS]
@@ -92,8 +100,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   uint64_t* ldbar = accdone + 4;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, i0 = a.row0 + blockIdx.x * TK_ROWS;
-  const int rows_valid = min(TK_ROWS, a.row1 - i0);
+  const int b = blockIdx.y, i0 = a.row0 + blockIdx.x * ROWS;
+  const int rows_valid = min(ROWS, a.row1 - i0);
   const int nchunks = (Hp + TK_KC - 1) / TK_KC;
   const int nsl_last = (Hp - (nchunks - 1) * TK_KC) / 16;        // valid K slabs of the last chunk (Hp is a multiple of 16)
   const bool upd_feats = a.flags & EGNN_FLAG_UPDATE_FEATS, upd_coors = a.flags & EGNN_FLAG_UPDATE_COORS;
@@ -104,9 +112,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     tc::mbar_init(ldbar, 1);
     tc::mbar_fence_init();
   }
-  if (warp == 0) tc::tmem_alloc<512>(&misc[0]);
+  if (warp == 0) tc::tmem_alloc<TK_TMEM>(&misc[0]);
   for (int x = tid; x < TP_EPI_FLOATS; x += TK_THREADS) epi[x] = a.epi[x];
-  for (int x = tid + rows_valid * Hp; x < TK_ROWS * Hp; x += TK_THREADS) As[x] = 0.f;
+  for (int x = tid + rows_valid * Hp; x < ROWS * Hp; x += TK_THREADS) As[x] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -242,47 +250,50 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
     const uint32_t ta = tm_wg + 16 + slot * 32;
     const bool more = NSLC != 0 && c + 1 < nchunks;
     const int nsl = NSLC ? NSLC : nsl_last, nsl_next = c + 2 == nchunks ? nsl_last : 4;
+    // Slab-major: the broadcast operands of a slab (A', w_d, edge-channel weights; 16 bytes per lane each, and every
+    // LDS.128 costs four L1 wavefronts whatever the overlap between lanes) are fetched ONCE and used for all four slots of
+    // the thread -- the kernel is bound by L1 wavefronts (ncu: 85 % of peak, 70 % of them these loads), not by the MUFU
+    // pipe.  The slot is therefore waited for at the top and every (half, slab) fragment goes to TMEM as soon as it is packed.
+    tc::mbar_wait(&empty[g * TK_SLOTS + slot], (((uint32_t)c / TK_SLOTS) & 1) ^ 1);
+    tc::tc_fence_after();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t hp[16];
+    for (int sl = 0; sl < 4; ++sl) {
+      if (sl == 2) issue_pending();                         // chunk c-1's MMAs, if this warp has the duty (before the skip below)
+      if (NSLC == 0 && sl >= nsl) continue;                 // tail chunk: slabs beyond H are neither computed nor multiplied
+      const float4 av = *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16);
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!GEN) wv = *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4);
+      float zg[GEN ? 4 : 1][4];                              // generic: A' + sum_q Wq[q] s_q for the four slots
+      if (GEN) {
 #pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        if (NSLC == 0 && sl >= nsl) {                       // tail chunk: slabs beyond H are not computed (no MUFU work)
-          hp[sl * 4 + 0] = hp[sl * 4 + 1] = hp[sl * 4 + 2] = hp[sl * 4 + 3] = 0u;
-          continue;
-        }
-        const bool slv = sl < nsl;                          // (always true here; kept for the loads below)
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 av = slv ? *reinterpret_cast<const float4*>(Arow + c * TK_KC + sl * 16) : zero4;
-        const float4 wv = (slv && !GEN) ? *reinterpret_cast<const float4*>(wds + c * TK_KC + sl * 16 + lq * 4) : zero4;
-        float zg[2][4];                                      // generic: A' + sum_q Wq[q] s_q for the two slots of this half
-        if (GEN) {
-#pragma unroll
-          for (int r2 = 0; r2 < 2; ++r2) { zg[r2][0] = av.x; zg[r2][1] = av.y; zg[r2][2] = av.z; zg[r2][3] = av.w; }
-          if (slv) {
+        for (int rho = 0; rho < 4; ++rho) { zg[GEN ? rho : 0][0] = av.x; zg[GEN ? rho : 0][1] = av.y; zg[GEN ? rho : 0][2] = av.z; zg[GEN ? rho : 0][3] = av.w; }
 #pragma unroll 1
-            for (int q = 0; q < Q; ++q) {
-              const float4 wq4 = *reinterpret_cast<const float4*>(wds + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
-              const float s0 = myS[q * 32 + lr + 16 * half], s1 = myS[q * 32 + lr + 16 * half + 8];
-              zg[0][0] = fmaf(wq4.x, s0, zg[0][0]); zg[0][1] = fmaf(wq4.y, s0, zg[0][1]);
-              zg[0][2] = fmaf(wq4.z, s0, zg[0][2]); zg[0][3] = fmaf(wq4.w, s0, zg[0][3]);
-              zg[1][0] = fmaf(wq4.x, s1, zg[1][0]); zg[1][1] = fmaf(wq4.y, s1, zg[1][1]);
-              zg[1][2] = fmaf(wq4.z, s1, zg[1][2]); zg[1][3] = fmaf(wq4.w, s1, zg[1][3]);
-            }
+        for (int q = 0; q < Q; ++q) {
+          const float4 wq4 = *reinterpret_cast<const float4*>(wds + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
+#pragma unroll
+          for (int rho = 0; rho < 4; ++rho) {
+            const float sq = myS[q * 32 + lr + 8 * rho];
+            float (&zz)[4] = zg[GEN ? rho : 0];
+            zz[0] = fmaf(wq4.x, sq, zz[0]); zz[1] = fmaf(wq4.y, sq, zz[1]);
+            zz[2] = fmaf(wq4.z, sq, zz[2]); zz[3] = fmaf(wq4.w, sq, zz[3]);
           }
         }
-        float4 we[TK_QE];
-        if (EDGES) {
+      }
+      float4 we[TK_QE];
+      if (EDGES) {
 #pragma unroll
-          for (int q = 0; q < TK_QE; ++q) we[q] = slv ? *reinterpret_cast<const float4*>(wes + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4) : zero4;
-        }
+        for (int q = 0; q < TK_QE; ++q) we[q] = *reinterpret_cast<const float4*>(wes + (size_t)q * Hp + c * TK_KC + sl * 16 + lq * 4);
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t h4[4];
 #pragma unroll
         for (int r2 = 0; r2 < 2; ++r2) {
           const int rho = half * 2 + r2;
           const uint2 bb = Bc[rho][sl];
           const float d = dr[rho];
           float z0 = fmaf(wv.x, d, av.x), z1 = fmaf(wv.y, d, av.y), z2 = fmaf(wv.z, d, av.z), z3 = fmaf(wv.w, d, av.w);
-          if (GEN) { z0 = zg[r2][0]; z1 = zg[r2][1]; z2 = zg[r2][2]; z3 = zg[r2][3]; }
+          if (GEN) { z0 = zg[GEN ? rho : 0][0]; z1 = zg[GEN ? rho : 0][1]; z2 = zg[GEN ? rho : 0][2]; z3 = zg[GEN ? rho : 0][3]; }
           if (EDGES) {
 #pragma unroll
             for (int q = 0; q < TK_QE; ++q) {
@@ -292,17 +303,13 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
           }
           const float y0 = tc::add_bf16_lo(bb.x, z0), y1 = tc::add_bf16_hi(bb.x, z1);
           const float y2 = tc::add_bf16_lo(bb.y, z2), y3 = tc::add_bf16_hi(bb.y, z3);
-          hp[sl * 4 + r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
-          hp[sl * 4 + r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
+          h4[r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
+          h4[r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
           if (more && sl < nsl_next) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
         }
+        // 16x256b fragment of slab sl: registers {0,1} -> slot lr (+16), {2,3} -> slot lr + 8 (+24)
+        tc::tmem_st_16x256b_x1(ta + ((uint32_t)(half * 16) << 16) + sl * 8, h4[0], h4[1], h4[2], h4[3]);
       }
-      if (half == 0) {
-        issue_pending();
-        tc::mbar_wait(&empty[g * TK_SLOTS + slot], (((uint32_t)c / TK_SLOTS) & 1) ^ 1);
-        tc::tc_fence_after();
-      }
-      tc::tmem_st_16x256b_x4(ta + ((uint32_t)(half * 16) << 16), hp);
     }
     tc::tmem_wait_st();
     tc::tc_fence_before();
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1) tc_knn_kernel(const TcKnnArgs a
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<512>(tmem);
+  if (warp == 0) tc::tmem_dealloc<TK_TMEM>(tmem);
 }
 
 }  // namespace egnn

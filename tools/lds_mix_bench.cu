@@ -44,12 +44,24 @@ __device__ __forceinline__ void four(float4 av, float4 wv, float d, uint2 bb, ui
   acc ^= p0 + p1;
 }
 
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(const void* p) {
+  uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ float lds32(const float* p) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
 __device__ __forceinline__ float4 bf4(uint2 v) {
   return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
 }
 
 template <int L>
-__global__ void __launch_bounds__(512) kround(float* out, int iters, float seed, int H) {
+__global__ void __launch_bounds__(512) kround(float* out, int iters, float seed, int H, int zero) {
   extern __shared__ __align__(16) unsigned char smraw[];
   float* Ab = reinterpret_cast<float*>(smraw);           // [4][H]  A' rows of the item
   float* wq = Ab + 4 * 4096;                             // [H]     w_d
@@ -74,25 +86,26 @@ __global__ void __launch_bounds__(512) kround(float* out, int iters, float seed,
     float4 ha[4], hw[4];
     if (L == 2) {
 #pragma unroll
-      for (int s = 0; s < 4; ++s) { ha[s] = *reinterpret_cast<const float4*>(Ai + s * 16); hw[s] = *reinterpret_cast<const float4*>(wi + s * 16); }
+      for (int s = 0; s < 4; ++s) { ha[s] = lds128(Ai + s * 16); hw[s] = lds128(wi + s * 16); }
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
+        const int ho = half * zero;          // runtime 0: keeps the two halves' loads distinct instructions, as in the kernel
         float4 av, wv;
         if (L == 0) { av = ra[s]; wv = rw[s]; }
-        else if (L == 1) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = *reinterpret_cast<const volatile float4*>(wi + s * 16); }
+        else if (L == 1) { av = lds128(Ai + s * 16 + ho); wv = lds128(wi + s * 16 + ho); }
         else if (L == 2) { av = ha[s]; wv = hw[s]; }
-        else if (L == 3) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = *reinterpret_cast<const float4*>(c_wd + c * 64 + lq * 4 + s * 16); }
+        else if (L == 3) { av = lds128(Ai + s * 16 + ho); wv = *reinterpret_cast<const float4*>(c_wd + c * 64 + lq * 4 + s * 16 + ho); }
         else if (L == 4) {
-          const uint2 a2 = *reinterpret_cast<const volatile uint2*>(reinterpret_cast<const __nv_bfloat16*>(Ab) + i * 4096 + c * 64 + lq * 4 + s * 16);
-          const uint2 w2 = *reinterpret_cast<const volatile uint2*>(reinterpret_cast<const __nv_bfloat16*>(wq) + c * 64 + lq * 4 + s * 16);
+          const uint2 a2 = lds64(reinterpret_cast<const __nv_bfloat16*>(Ab) + i * 4096 + c * 64 + lq * 4 + s * 16 + ho);
+          const uint2 w2 = lds64(reinterpret_cast<const __nv_bfloat16*>(wq) + c * 64 + lq * 4 + s * 16 + ho);
           av = bf4(a2); wv = bf4(w2);
-        } else if (L == 5) { av = *reinterpret_cast<const volatile float4*>(Ai + s * 16); wv = rw[s]; }
+        } else if (L == 5) { av = lds128(Ai + s * 16 + ho); wv = rw[s]; }
         else {
-          const volatile float* pa = Ai + s * 16; const volatile float* pw = wi + s * 16;
-          av = make_float4(pa[0], pa[1], pa[2], pa[3]); wv = make_float4(pw[0], pw[1], pw[2], pw[3]);
+          const float* pa = Ai + s * 16 + ho; const float* pw = wi + s * 16 + ho;
+          av = make_float4(lds32(pa), lds32(pa + 1), lds32(pa + 2), lds32(pa + 3)); wv = make_float4(lds32(pw), lds32(pw + 1), lds32(pw + 2), lds32(pw + 3));
         }
 #pragma unroll
         for (int r2 = 0; r2 < 2; ++r2) four(av, wv, dr[half * 2 + r2], Bc[half * 2 + r2][s], acc);
@@ -107,10 +120,10 @@ static float* g_out; static int g_sms;
 template <int L> double run(int iters, int warps_per_smsp) {
   cudaFuncSetAttribute(kround<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int ctas = g_sms * (warps_per_smsp / 4);
-  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, 64, 1.0f, 2048);
+  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, 64, 1.0f, 2048, 0);
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   cudaEventRecord(a);
-  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, iters, 1.0f, 2048);
+  kround<L><<<ctas, 512, 100 * 1024>>>(g_out, iters, 1.0f, 2048, 0);
   cudaEventRecord(b); cudaEventSynchronize(b);
   float ms; cudaEventElapsedTime(&ms, a, b);
   return ms;
