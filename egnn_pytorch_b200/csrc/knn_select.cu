@@ -89,9 +89,12 @@ inline size_t sel_smem_bytes(int C, int warps = SEL_WARPS_MAX) {
   return (size_t)C * SEL_JC * sizeof(T) + SEL_JC + (size_t)warps * 64 * (sizeof(T) + sizeof(int)) + 64;
 }
 
-template <typename T, int SEL_WARPS>
+// CDIM = 3: the coordinate loops are exactly three steps (the generic instantiation, CDIM = 0, issues all eight predicated
+// steps per candidate -- 125 instead of ~55 instructions per trip of the scan, which is 63 % of the kernel; ncu source page)
+template <typename T, int SEL_WARPS, int CDIM>
 __global__ void __launch_bounds__(SEL_WARPS * 32)
 knn_warp_select_kernel(const SelArgs<T> a) {
+  constexpr int NC = CDIM ? CDIM : 8;
   extern __shared__ __align__(16) unsigned char sel_sm[];
   T* xs = reinterpret_cast<T*>(sel_sm);                                   // [C][JC]
   T* qkey = xs + (size_t)a.C * SEL_JC;                                    // [WARPS][64]
@@ -103,9 +106,9 @@ knn_warp_select_kernel(const SelArgs<T> a) {
   const bool rv = iraw < a.N;
   const int i = rv ? iraw : a.N - 1;
   const size_t row = (size_t)b * a.N + i;
-  T xi[8];
+  T xi[NC];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) xi[c] = c < a.C ? a.coors[row * a.C + c] : T(0);
+  for (int c = 0; c < NC; ++c) xi[c] = (CDIM || c < a.C) ? a.coors[row * a.C + c] : T(0);
   const bool mask_i = a.mask ? a.mask[row] != 0 : true;
   const uint8_t* adjrow = a.adj ? a.adj + ((size_t)(a.adj_batched ? b : 0) * a.N + i) * a.N : nullptr;
   const T INF = T(INFINITY);
@@ -123,8 +126,8 @@ knn_warp_select_kernel(const SelArgs<T> a) {
     for (int jj = threadIdx.x; jj < jn; jj += SEL_WARPS * 32) {          // one candidate per thread: no index division
       const T* src = a.coors + ((size_t)b * a.N + jc0 + jj) * a.C;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < a.C) xs[c * SEL_JC + jj] = src[c];
+      for (int c = 0; c < NC; ++c)
+        if (CDIM || c < a.C) xs[c * SEL_JC + jj] = src[c];
       if (a.mask) ms[jj] = a.mask[(size_t)b * a.N + jc0 + jj];
     }
     __syncthreads();
@@ -142,8 +145,8 @@ knn_warp_select_kernel(const SelArgs<T> a) {
         if (jvalid) {
           T d = T(0);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            if (c < a.C) d = sq_acc<T>(xi[c] - xs[c * SEL_JC + jj], d);
+          for (int c = 0; c < NC; ++c)
+            if (CDIM || c < a.C) d = sq_acc<T>(xi[c] - xs[c * SEL_JC + jj], d);
           if (a.mask && !(mask_i && ms[jj])) d = T(1e5);
           if (adjrow) {
             if (i == j) d = T(-1);
@@ -247,19 +250,22 @@ static int launch_select(int B, int N, int C, int k, const void* coors, const ui
     int dev = 0;
     EGNN_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sel_smem_bytes<T>(8, 16)));
-      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      EGNN_CUDA_TRY(cudaFuncSetAttribute(knn_warp_select_kernel<T, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sel_smem_bytes<T>(8, 8)));
       attr_set[dev] = true;
     }
     // 16 rows per CTA halve the staging work per row; small problems keep 8 so that more SMs take part
-    if ((long)B * ceil_div(N, 16) >= 296) {
-      dim3 grid(ceil_div(N, 16), B);
-      knn_warp_select_kernel<T, 16><<<grid, 16 * 32, sel_smem_bytes<T>(C, 16), st>>>(a);
+    const bool wide = (long)B * ceil_div(N, 16) >= 296;
+    dim3 grid(ceil_div(N, wide ? 16 : 8), B);
+    const size_t smem = sel_smem_bytes<T>(C, wide ? 16 : 8);
+    if (C == 3) {
+      if (wide) knn_warp_select_kernel<T, 16, 3><<<grid, 16 * 32, smem, st>>>(a);
+      else knn_warp_select_kernel<T, 8, 3><<<grid, 8 * 32, smem, st>>>(a);
     } else {
-      dim3 grid(ceil_div(N, 8), B);
-      knn_warp_select_kernel<T, 8><<<grid, 8 * 32, sel_smem_bytes<T>(C, 8), st>>>(a);
+      if (wide) knn_warp_select_kernel<T, 16, 0><<<grid, 16 * 32, smem, st>>>(a);
+      else knn_warp_select_kernel<T, 8, 0><<<grid, 8 * 32, smem, st>>>(a);
     }
   } else {
     int Npad = 1;

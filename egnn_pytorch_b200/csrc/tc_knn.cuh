@@ -292,19 +292,29 @@ __global__ void __launch_bounds__(ROWS * 32, ROWS == 8 ? 2 : 1) tc_knn_kernel(co
           const int rho = half * 2 + r2;
           const uint2 bb = Bc[rho][sl];
           const float d = dr[rho];
-          float z0 = fmaf(wv.x, d, av.x), z1 = fmaf(wv.y, d, av.y), z2 = fmaf(wv.z, d, av.z), z3 = fmaf(wv.w, d, av.w);
-          if (GEN) { z0 = zg[GEN ? rho : 0][0]; z1 = zg[GEN ? rho : 0][1]; z2 = zg[GEN ? rho : 0][2]; z3 = zg[GEN ? rho : 0][3]; }
+          // packed FFMA2 (two channels per instruction) for w_d d + A', the edge channels and y + y tanh y
+          float2 z01, z23;
+          if (GEN) {
+            z01 = make_float2(zg[GEN ? rho : 0][0], zg[GEN ? rho : 0][1]); z23 = make_float2(zg[GEN ? rho : 0][2], zg[GEN ? rho : 0][3]);
+          } else {
+            const float2 dd = make_float2(d, d);
+            z01 = tc::ffma2(make_float2(wv.x, wv.y), dd, make_float2(av.x, av.y));
+            z23 = tc::ffma2(make_float2(wv.z, wv.w), dd, make_float2(av.z, av.w));
+          }
           if (EDGES) {
 #pragma unroll
             for (int q = 0; q < TK_QE; ++q) {
-              const float e = ef[rho][q];
-              z0 = fmaf(we[q].x, e, z0); z1 = fmaf(we[q].y, e, z1); z2 = fmaf(we[q].z, e, z2); z3 = fmaf(we[q].w, e, z3);
+              const float2 ee = make_float2(ef[rho][q], ef[rho][q]);
+              z01 = tc::ffma2(make_float2(we[q].x, we[q].y), ee, z01);
+              z23 = tc::ffma2(make_float2(we[q].z, we[q].w), ee, z23);
             }
           }
-          const float y0 = tc::add_bf16_lo(bb.x, z0), y1 = tc::add_bf16_hi(bb.x, z1);
-          const float y2 = tc::add_bf16_lo(bb.y, z2), y3 = tc::add_bf16_hi(bb.y, z3);
-          h4[r2 * 2 + 0] = tc::pack_bf16x2(tc::silu_half_arg(y0), tc::silu_half_arg(y1));
-          h4[r2 * 2 + 1] = tc::pack_bf16x2(tc::silu_half_arg(y2), tc::silu_half_arg(y3));
+          const float2 y01 = make_float2(tc::add_bf16_lo(bb.x, z01.x), tc::add_bf16_hi(bb.x, z01.y));
+          const float2 y23 = make_float2(tc::add_bf16_lo(bb.y, z23.x), tc::add_bf16_hi(bb.y, z23.y));
+          const float2 h01 = tc::ffma2(y01, make_float2(tc::tanh_fast(y01.x), tc::tanh_fast(y01.y)), y01);
+          const float2 h23 = tc::ffma2(y23, make_float2(tc::tanh_fast(y23.x), tc::tanh_fast(y23.y)), y23);
+          h4[r2 * 2 + 0] = tc::pack_bf16x2(h01.x, h01.y);
+          h4[r2 * 2 + 1] = tc::pack_bf16x2(h23.x, h23.y);
           if (more && sl < nsl_next) Bc[rho][sl] = __ldg(Bp[rho] + (c + 1) * 16 + sl * 4);
         }
         // 16x256b fragment of slab sl: registers {0,1} -> slot lr (+16), {2,3} -> slot lr + 8 (+24)
