@@ -46,11 +46,12 @@ def exists(v):
 # ----------------------------------------------------------------------------- runtime helpers
 
 _WORKSPACES: dict = {}
+_NULL_CTX = contextlib.nullcontext()
 
 
-def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+def _workspace(device: torch.device, nbytes: int, stream_handle=None) -> torch.Tensor:
     """Per-(device, stream) scratch arena, grown on demand; the library never allocates."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream if stream_handle is None else stream_handle)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -67,6 +68,7 @@ def _compute_device(t: torch.Tensor) -> torch.device:
 
 
 _KERNEL_DTYPE = {torch.float32: nat.DTYPE_F32, torch.float64: nat.DTYPE_F64, torch.bfloat16: nat.DTYPE_BF16}
+_PATH_NAME = {torch.float64: "fp64-simt", torch.float32: "fp32-simt", torch.bfloat16: "bf16-tcgen05"}
 
 
 def _ptr(t):
@@ -246,7 +248,7 @@ class EGNN(nn.Module):
 
     def _staged(self, device, dtype):
         fields = self._state_fields()
-        sig = tuple((p.data_ptr(), p._version) for _, _, _, p in fields)
+        sig = [x for _, _, _, p in fields for x in (p.data_ptr(), p._version)]
         key = (device, dtype)
         st = self._stage.get(key)
         always = self.cache_policy == "always" or (self.training and any(p.requires_grad for _, _, _, p in fields))
@@ -258,6 +260,9 @@ class EGNN(nn.Module):
         return st
 
     def _flags(self):
+        fl = self.__dict__.get("_flags_cache")
+        if fl is not None:
+            return fl
         fl = 0
         if isinstance(self.node_norm, nn.LayerNorm): fl |= nat.FLAG_NORM_FEATS
         if isinstance(self.coors_norm, CoorsNorm): fl |= nat.FLAG_NORM_COORS
@@ -266,10 +271,14 @@ class EGNN(nn.Module):
         if self.edge_gate is not None: fl |= nat.FLAG_SOFT_EDGES
         if self.m_pool_method == "mean": fl |= nat.FLAG_POOL_MEAN
         if self.coor_weights_clamp_value is not None: fl |= nat.FLAG_CLAMP
+        self.__dict__["_flags_cache"] = fl       # the sub-modules tested above are fixed by the constructor
         return fl
 
     def _kernel_dtype(self):
-        pd = self.edge_mlp[0].weight.dtype
+        lin0 = self.__dict__.get("_lin0")
+        if lin0 is None:
+            lin0 = self.__dict__["_lin0"] = self.edge_mlp[0]       # plain reference (not a registered sub-module)
+        pd = lin0.weight.dtype
         if pd == torch.float64:
             return torch.float64
         prec = os.environ.get("EGNN_B200_PRECISION", self.precision)
@@ -285,16 +294,16 @@ class EGNN(nn.Module):
         `neighbors` (additive, keyword-only): int tensor [B, N, k] of neighbour indices, -1 = empty slot.  When
         given, the layer runs on exactly these edges and the O(N^2) distance / top-k pass is skipped -- the
         edge-list mode of SURVEY.md section 8(f) (`edge_index_to_neighbors` converts a PyG-style edge_index)."""
-        fields = self._state_fields()
-        train = torch.is_grad_enabled() and (
-            feats.requires_grad or coors.requires_grad or (edges is not None and edges.requires_grad) or
-            (_label_emb is not None and _label_emb.requires_grad) or any(p.requires_grad for _, _, _, p in fields))
-        if train:
-            return self._forward_train(fields, feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb,
-                                       _k_hint, _rows)
-        with torch.no_grad():
-            return self._forward_impl(feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb, _k_hint,
-                                      _rows)
+        if torch.is_grad_enabled():             # (the parameter scan is skipped entirely under torch.no_grad())
+            fields = self._state_fields()
+            if (feats.requires_grad or coors.requires_grad or (edges is not None and edges.requires_grad) or
+                    (_label_emb is not None and _label_emb.requires_grad) or any(p.requires_grad for _, _, _, p in fields)):
+                return self._forward_train(fields, feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb,
+                                           _k_hint, _rows)
+            with torch.no_grad():
+                return self._forward_impl(feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb, _k_hint,
+                                          _rows)
+        return self._forward_impl(feats, coors, edges, mask, adj_mat, neighbors, _edge_labels, _label_emb, _k_hint, _rows)
 
     def _forward_train(self, fields, feats, coors, edges, mask, adj_mat, neighbors, labels, label_emb, k_hint, rows):
         if rows is not None:
@@ -414,8 +423,9 @@ class EGNN(nn.Module):
             st["wstruct"] = {wkey: w}
             st["lab_keepalive"] = lab_w
 
-        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        ctx = contextlib.nullcontext() if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+        stream_handle = torch.cuda.current_stream(dev).cuda_stream
+        stream = C.c_void_p(stream_handle)
+        ctx = _NULL_CTX if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
         with ctx:
             # packed parameters, cached until a parameter changes
             pkey = (label_dim, 0 if lab_w is None else (label_emb.data_ptr(), label_emb._version))
@@ -443,23 +453,30 @@ class EGNN(nn.Module):
                 nbytes = b * n * (k if k > 0 else n) * mp * f_in.element_size()
                 if nbytes <= float(os.environ.get("EGNN_B200_SAVE_PAIR_MB", "1024")) * 2 ** 20:
                     pre2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            io = nat.LayerIO(feats=f_in.data_ptr(), coors=x_in.data_ptr(), edges=None if e_in is None else e_in.data_ptr(),
-                             edge_labels=None if l_in is None else l_in.data_ptr(),
-                             mask=None if m_in is None else m_in.data_ptr(),
-                             adj=None if adj_u8 is None else adj_u8.data_ptr(),
-                             feats_out=f_out.data_ptr(), coors_out=x_out.data_ptr(),
-                             nbr_idx=None if nbr is None else nbr.data_ptr(),
-                             pre2_out=None if pre2 is None else pre2.data_ptr())
+            # the library reads EgnnLayerIO during the call only: inference re-fills one struct per layer, training
+            # (which keeps it with the saved state) gets its own
+            io = nat.LayerIO() if train else self.__dict__.get("_io_scratch")
+            if io is None:
+                io = self.__dict__["_io_scratch"] = nat.LayerIO()
+            io.feats = f_in.data_ptr(); io.coors = x_in.data_ptr()
+            io.edges = None if e_in is None else e_in.data_ptr()
+            io.edge_labels = None if l_in is None else l_in.data_ptr()
+            io.mask = None if m_in is None else m_in.data_ptr()
+            io.adj = None if adj_u8 is None else adj_u8.data_ptr()
+            io.feats_out = f_out.data_ptr(); io.coors_out = x_out.data_ptr()
+            io.nbr_idx = None if nbr is None else nbr.data_ptr()
+            io.pre2_out = None if pre2 is None else pre2.data_ptr()
             if train:     # preflight: configurations the backward kernels cannot run fail HERE, before the forward launches
                 nbb = C.c_size_t()
                 nat.check("egnn_layer_backward_workspace_bytes", lib.egnn_layer_backward_workspace_bytes(C.byref(desc), C.byref(nbb)))
             # training keeps the workspace (per-node tables, pooled messages, neighbour lists) for backward
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if train else _workspace(dev, ws_bytes)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if train else _workspace(dev, ws_bytes, stream_handle)
             nat.check("egnn_layer_forward",
                       lib.egnn_layer_forward(C.byref(desc), C.byref(w), _ptr(packed), C.byref(io), _ptr(ws),
                                              ws.numel(), stream))
-        self.last_path = {torch.float64: "fp64-simt", torch.float32: "fp32-simt", torch.bfloat16: "bf16-tcgen05"}[kdt]
-        outs = (f_out.to(device=feats.device, dtype=feats.dtype), x_out.to(device=coors.device, dtype=coors.dtype))
+        object.__setattr__(self, "last_path", _PATH_NAME[kdt])
+        outs = (f_out if (f_out.dtype == feats.dtype and f_out.device == feats.device) else f_out.to(device=feats.device, dtype=feats.dtype),
+                x_out if (x_out.dtype == coors.dtype and x_out.device == coors.device) else x_out.to(device=coors.device, dtype=coors.dtype))
         if not train:
             return outs
         saved = dict(dev=dev, kdt=kdt, cdt=cdt, desc=desc, w=w, packed=packed, io=io, ws=ws, tensors=T,
@@ -645,7 +662,7 @@ class EGNN_Network(nn.Module):
             tok = feats.to(torch.int64).contiguous()
             n = tok.shape[1]
             feats = torch.empty((b, n, tw.shape[1]), dtype=tw.dtype, device=dev)
-            with torch.cuda.device(dev):
+            with (_NULL_CTX if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)):
                 nat.check("egnn_embed_nodes", lib.egnn_embed_nodes(
                     _KERNEL_DTYPE[tw.dtype], b, n, tw.shape[1], tw.shape[0], _ptr(tok), _ptr(tw), _ptr(pw), _ptr(feats),
                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
@@ -697,7 +714,8 @@ class EGNN_Network(nn.Module):
                                 _k_hint=k_hint)
             coor_changes.append(coors)
 
-        feats, coors = feats.to(out_dev), coors.to(out_dev)
+        if out_dev != dev:
+            feats, coors = feats.to(out_dev), coors.to(out_dev)
         if return_coor_changes:
             return feats, coors, [c.to(out_dev) for c in coor_changes]
         return feats, coors
