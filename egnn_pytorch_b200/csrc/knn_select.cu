@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(256) adj_neighbors_kernel(int B, int N, int k,
     }
   }
   pos = pos < k ? pos : k;
-  for (int p = pos + lane; p < k; p += 32) { oi[p] = i; if (ok) ok[p] = 0; }
+  // unused slots: the node itself with ok = 0, or -1 (the edge-list convention of EgnnLayerIO.nbr_idx) when no ok array is kept
+  for (int p = pos + lane; p < k; p += 32) { oi[p] = ok ? i : -1; if (ok) ok[p] = 0; }
 }
 
 int adj_neighbors_dispatch(int B, int N, int k, const uint8_t* adj, int adj_batched, int32_t* out_idx, uint8_t* out_ok,
@@ -357,4 +358,9 @@ extern "C" int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, i
                                double valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream) {
   return egnn::knn_select_dispatch(dtype, B, N, C, k, coors, mask, adj, adj_batched, valid_radius, out_idx,
                                    out_ok, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int egnn_adj_neighbors(int32_t B, int32_t N, int32_t k, const uint8_t* adj, int32_t adj_batched, int32_t* out_idx,
+                                  uint8_t* out_ok, void* stream) {
+  return egnn::adj_neighbors_dispatch(B, N, k, adj, adj_batched, out_idx, out_ok, static_cast<cudaStream_t>(stream));
 }

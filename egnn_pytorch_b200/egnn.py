@@ -674,7 +674,7 @@ class EGNN_Network(nn.Module):
         if exists(edges) and exists(self.edge_emb):
             edges = F.embedding(edges, staged(self.edge_emb))                        # :410-411
 
-        labels = label_emb = k_hint = None
+        labels = label_emb = k_hint = nbr_lists = None
         if exists(self.num_adj_degrees):
             assert exists(adj_mat), "adjacency matrix must be passed in (keyword argument adj_mat)"
             # the expansion depends on the adjacency only: cached per (storage, version), which also keeps the
@@ -695,9 +695,18 @@ class EGNN_Network(nn.Module):
                         b, n, self.num_adj_degrees, _ptr(adj_in), 1 if adj_in.dim() == 3 else 0, _ptr(adj_out), _ptr(lab),
                         _ptr(max_sum), _ptr(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
                 kmax = int(max_sum.item()) if self.layers[0][1].only_sparse_neighbors else None   # the reference's sync at :249
-                cached = (akey, adj_out, lab, kmax, adj_mat)     # adj_mat kept alive so the key cannot be recycled
+                # only_sparse_neighbors with a node mask: the surviving slots of every layer's top-k are the node and its
+                # adjacent nodes (valid_radius = 0, :250, :296) -- lists that depend on the adjacency only.  Built once
+                # here (egnn_adj_neighbors) and handed to every layer instead of one adjacency scan per layer.
+                lists = None
+                if kmax is not None and 0 < kmax <= n and os.environ.get("EGNN_B200_NO_LIST_CACHE") != "1":
+                    lists = torch.empty((b, n, kmax), dtype=torch.int32, device=dev)
+                    with torch.cuda.device(dev):
+                        nat.check("egnn_adj_neighbors", lib.egnn_adj_neighbors(
+                            b, n, kmax, _ptr(adj_out), 1, _ptr(lists), None, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+                cached = (akey, adj_out, lab, kmax, adj_mat, lists)     # adj_mat kept alive so the key cannot be recycled
                 self.__dict__["_adj_cache"] = cached
-            _, adj_out, lab, k_hint, _ = cached
+            _, adj_out, lab, k_hint, _, nbr_lists = cached
             adj_mat = adj_out                                                        # layers see the expanded matrix (:428, :448)
             if exists(self.adj_emb):
                 labels, label_emb = lab, self.adj_emb.weight
@@ -711,7 +720,7 @@ class EGNN_Network(nn.Module):
             if exists(global_attn):
                 feats, global_tokens = global_attn(feats, global_tokens, mask=mask)
             feats, coors = egnn(feats, coors, edges, mask, adj_mat, _edge_labels=labels, _label_emb=label_emb,
-                                _k_hint=k_hint)
+                                _k_hint=k_hint, neighbors=nbr_lists if exists(mask) else None)
             coor_changes.append(coors)
 
         if out_dev != dev:

@@ -204,6 +204,15 @@ int egnn_knn_select(int32_t dtype, int32_t B, int32_t N, int32_t C, int32_t k,
                     const void* coors, const uint8_t* mask, const uint8_t* adj, int32_t adj_batched,
                     double valid_radius, int32_t* out_idx, uint8_t* out_ok, void* stream);
 
+/* Neighbour lists from an adjacency alone: slot 0 = the node itself, then its adjacent nodes in ascending index order,
+ * truncated at k -- exactly the slots of egnn_knn_select whose rank is <= 0 (egnn_pytorch.py:255-256), i.e. every slot that
+ * survives `only_sparse_neighbors` with a node mask (valid_radius = 0, :250, :296).  They do not depend on the coordinates,
+ * so EGNN_Network builds them once per adjacency and hands them to every layer (EgnnLayerIO.nbr_idx).
+ * adj [N,N] or [B,N,N] 0/1 bytes; out_idx int32 [B,N,k]; out_ok uint8 [B,N,k] or NULL.  Unused slots: the node itself with
+ * ok = 0, or -1 when out_ok is NULL. */
+int egnn_adj_neighbors(int32_t B, int32_t N, int32_t k, const uint8_t* adj, int32_t adj_batched, int32_t* out_idx,
+                       uint8_t* out_ok, void* stream);
+
 /* N-th degree adjacency of EGNN_Network (egnn_pytorch.py:414-428) without the dense A@A:
  * adj_in [N,N] or [B,N,N] 0/1; writes the expanded adjacency adj_out [B,N,N] 0/1, the degree
  * labels labels_out [B,N,N] (0 = not connected, d = first reached in round d) and

@@ -1,9 +1,10 @@
-"""Summarise an .ncu-rep (first kernel) into the handful of numbers DESIGN.md / profiles/ cite."""
+"""Summarise one kernel of an .ncu-rep (argv[2] = index of the profiled launch, default 0) into the handful of numbers
+DESIGN.md / profiles/ cite."""
 import csv, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[2]) if len(sys.argv) > 2 else 0)]
 d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
