@@ -261,24 +261,21 @@ class EGNN(nn.Module):
 
     def _flags(self):
         fl = self.__dict__.get("_flags_cache")
-        if fl is not None:
-            return fl
-        fl = 0
-        if isinstance(self.node_norm, nn.LayerNorm): fl |= nat.FLAG_NORM_FEATS
-        if isinstance(self.coors_norm, CoorsNorm): fl |= nat.FLAG_NORM_COORS
-        if self.node_mlp is not None: fl |= nat.FLAG_UPDATE_FEATS
-        if self.coors_mlp is not None: fl |= nat.FLAG_UPDATE_COORS
-        if self.edge_gate is not None: fl |= nat.FLAG_SOFT_EDGES
+        if fl is None:                           # which sub-modules exist is fixed by the constructor
+            fl = 0
+            if isinstance(self.node_norm, nn.LayerNorm): fl |= nat.FLAG_NORM_FEATS
+            if isinstance(self.coors_norm, CoorsNorm): fl |= nat.FLAG_NORM_COORS
+            if self.node_mlp is not None: fl |= nat.FLAG_UPDATE_FEATS
+            if self.coors_mlp is not None: fl |= nat.FLAG_UPDATE_COORS
+            if self.edge_gate is not None: fl |= nat.FLAG_SOFT_EDGES
+            self.__dict__["_flags_cache"] = fl
+        # plain attributes a user may change between calls are read every time
         if self.m_pool_method == "mean": fl |= nat.FLAG_POOL_MEAN
         if self.coor_weights_clamp_value is not None: fl |= nat.FLAG_CLAMP
-        self.__dict__["_flags_cache"] = fl       # the sub-modules tested above are fixed by the constructor
         return fl
 
     def _kernel_dtype(self):
-        lin0 = self.__dict__.get("_lin0")
-        if lin0 is None:
-            lin0 = self.__dict__["_lin0"] = self.edge_mlp[0]       # plain reference (not a registered sub-module)
-        pd = lin0.weight.dtype
+        pd = self._modules["edge_mlp"]._modules["0"]._parameters["weight"].dtype     # edge_mlp[0].weight without three __getattr__ hops
         if pd == torch.float64:
             return torch.float64
         prec = os.environ.get("EGNN_B200_PRECISION", self.precision)
