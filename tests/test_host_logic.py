@@ -192,3 +192,23 @@ def test_training_path_selection_without_gpu(monkeypatch):
         layer.requires_grad_(True)
         layer(f, x)                                     # parameters require grad
     assert calls == ["infer", "infer", "train", "train"]
+
+
+def test_flags_follow_attributes_changed_after_construction(nat):
+    """Only the module structure is cached in the flag word: the pooling method and the clamp value are plain attributes
+    and a change between calls must reach the descriptor (reference reads them per call, egnn_pytorch.py:308, :319)."""
+    from egnn_pytorch_b200 import EGNN
+    layer = EGNN(dim=8, norm_feats=True, soft_edges=True)
+    f0 = layer._flags()
+    assert f0 & nat.FLAG_NORM_FEATS and f0 & nat.FLAG_SOFT_EDGES and f0 & nat.FLAG_UPDATE_FEATS and f0 & nat.FLAG_UPDATE_COORS
+    assert not f0 & nat.FLAG_CLAMP and not f0 & nat.FLAG_POOL_MEAN
+    layer.coor_weights_clamp_value = 2.0
+    layer.m_pool_method = "mean"
+    f1 = layer._flags()
+    assert f1 & nat.FLAG_CLAMP and f1 & nat.FLAG_POOL_MEAN and (f1 & f0) == f0
+    layer.coor_weights_clamp_value = None
+    assert not layer._flags() & nat.FLAG_CLAMP
+
+
+def test_native_symbol_table_has_adj_neighbors(nat):
+    assert "egnn_adj_neighbors" in nat.SYMBOLS and hasattr(nat.load(), "egnn_adj_neighbors")
