@@ -212,3 +212,30 @@ def test_flags_follow_attributes_changed_after_construction(nat):
 
 def test_native_symbol_table_has_adj_neighbors(nat):
     assert "egnn_adj_neighbors" in nat.SYMBOLS and hasattr(nat.load(), "egnn_adj_neighbors")
+
+
+def test_parameter_staging_cache_semantics():
+    """The staged / packed parameter copies are keyed on (storage pointer, version) of every parameter: an in-place
+    update, a replaced Parameter, `invalidate_cache()` and `cache_policy='always'` must each re-stage; nothing else may."""
+    from egnn_pytorch_b200 import EGNN
+    cpu = torch.device("cpu")
+    layer = EGNN(dim=8).eval()
+    s1 = layer._staged(cpu, torch.float32)
+    assert layer._staged(cpu, torch.float32) is s1                       # unchanged parameters: cache hit
+    w = layer.edge_mlp[0].weight
+    with torch.no_grad():
+        w.add_(1.0)                                                      # optimizer-style in-place step
+    s2 = layer._staged(cpu, torch.float32)
+    assert s2 is not s1 and torch.equal(s2["tensors"]["edge_w1"], w.detach())
+    layer.edge_mlp[0].weight = torch.nn.Parameter(torch.zeros_like(w))   # Parameter object replaced
+    s3 = layer._staged(cpu, torch.float32)
+    assert s3 is not s2 and float(s3["tensors"]["edge_w1"].abs().max()) == 0.0
+    layer.invalidate_cache()
+    s4 = layer._staged(cpu, torch.float32)
+    assert s4 is not s3
+    layer.cache_policy = "always"
+    assert layer._staged(cpu, torch.float32) is not s4
+    layer.cache_policy = "version"
+    s5 = layer._staged(cpu, torch.float32)
+    assert layer._staged(cpu, torch.float32) is s5
+    assert layer._staged(cpu, torch.float64) is not s5                   # one staging per (device, dtype)
